@@ -1,0 +1,154 @@
+/* bnpp_b200.h -- C ABI of the B200-native factor-algebra hot path of bn-pp.
+ *
+ * This is the drop-in boundary.  bn-pp has no FFI of its own: the
+ * boundary is what sits UNDER its public C++ classes `bn::Factor` / `bn::Domain`
+ * (code/factor.hh:10-48, code/domain.hh:11-45) and under the inner loops of
+ * `BN::variable_elimination` (code/model.cpp:348-446) and `FactorGraph::update`
+ * (code/graph.cpp:298-403).  Every entry point below names the reference code it
+ * replaces.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - All tables are dense fp64, row-major with the LAST scope variable fastest
+ *     (code/domain.cpp:20-24).  A scope is (rank, var_id[], card[]).
+ *   - `double *` table arguments are DEVICE pointers (from bnpp_alloc or any CUDA
+ *     allocation on the context's device, e.g. a torch tensor's data_ptr()).
+ *   - `z_dev`, when non-NULL, is a DEVICE pointer to one double that receives the
+ *     result's partition  Z = sum of its entries  (code/factor.cpp:139,172,204,234),
+ *     reduced in a fixed order (bit-stable across runs).
+ *   - Calls are asynchronous on the context's stream; bnpp_download and
+ *     bnpp_ctx_sync synchronise.  One host thread per context (SURVEY §8b threading).
+ *   - Every function returns 0 on success or a negative BNPP_E* code; no exceptions
+ *     cross the ABI.  bnpp_last_error gives the message.  There is NO CPU fallback:
+ *     without a usable CUDA device every compute call fails with BNPP_ECUDA.
+ */
+#ifndef BNPP_B200_H_
+#define BNPP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNPP_OK        0
+#define BNPP_EINVAL   -1   /* malformed scope / operand (variable in neither output nor eliminated, ...) */
+#define BNPP_ECUDA    -2   /* CUDA runtime error (message in bnpp_last_error) */
+#define BNPP_ERANK    -3   /* more than BNPP_MAX_AXES non-mergeable axes or BNPP_MAX_OPERANDS operands */
+#define BNPP_ETOOBIG  -4   /* a table has >= 2^32 entries (the reference's `unsigned` limit, code/domain.hh:41-42) */
+#define BNPP_ENOMEM   -5
+
+#define BNPP_MAX_RANK      64   /* scope width accepted at the ABI */
+#define BNPP_MAX_AXES      32   /* iteration axes left after merging contiguous ones */
+#define BNPP_MAX_OPERANDS   6   /* operands of one fused elimination step */
+
+/* status bits accumulated on the device, read with bnpp_ctx_status */
+#define BNPP_STATUS_ZERO_DIVISOR 1u   /* code/factor.cpp:169 asserts on this */
+
+typedef struct bnpp_ctx bnpp_ctx;
+
+/* Layout of a dense table: the reference's Domain (code/domain.cpp:15-26). */
+typedef struct {
+    int32_t rank;
+    const uint32_t *var_id;   /* [rank] scope order, last fastest */
+    const uint32_t *card;     /* [rank] */
+} bnpp_scope;
+
+/* One operand of a contraction: a (possibly strided / sliced / permuted) view of a
+ * device table.  stride == NULL means dense row-major over `scope`.  Evidence
+ * reduction (code/factor.cpp:214-242) is expressed as a view: observed axes are
+ * dropped from the scope and their offset folded into `data`. */
+typedef struct {
+    const double *data;
+    bnpp_scope scope;
+    const int64_t *stride;    /* [rank] in elements, or NULL */
+} bnpp_operand;
+
+/* ---- context, memory -------------------------------------------------------- */
+/* stream: a cudaStream_t to launch on (e.g. torch's current stream), or NULL to
+ * create a private non-blocking stream. */
+int bnpp_ctx_create(int device, void *stream, bnpp_ctx **out);
+int bnpp_ctx_destroy(bnpp_ctx *ctx);
+int bnpp_ctx_sync(bnpp_ctx *ctx);
+int bnpp_ctx_status(bnpp_ctx *ctx, uint32_t *status_bits, int clear);   /* synchronises */
+const char *bnpp_last_error(const bnpp_ctx *ctx);
+int bnpp_version(void);
+/* number of kernels this context has launched (bench.py's gpu_launches) */
+uint64_t bnpp_launch_count(const bnpp_ctx *ctx);
+/* name, grid and block of the most recent contraction launch (diagnostics / tests) */
+int bnpp_last_launch(const bnpp_ctx *ctx, char *name, size_t name_len, uint32_t *grid, uint32_t *block);
+
+int bnpp_alloc(bnpp_ctx *ctx, uint64_t n_doubles, double **dptr);     /* stream-ordered pool */
+int bnpp_free(bnpp_ctx *ctx, double *dptr);
+int bnpp_upload(bnpp_ctx *ctx, double *dst_dev, const double *src_host, uint64_t n);   /* async if src is pinned */
+int bnpp_download(bnpp_ctx *ctx, double *dst_host, const double *src_dev, uint64_t n); /* synchronises */
+int bnpp_fill(bnpp_ctx *ctx, double *dst_dev, uint64_t n, double value);   /* Factor(domain, value), code/factor.cpp:18-23 */
+
+/* ---- scope helpers (host only; no device needed) ------------------------------ */
+/* code/domain.cpp:32-52: d1 in order, then d2-only variables in d2 order.
+ * out arrays must hold a.rank + b.rank entries; returns the union rank. */
+int bnpp_union_scope(const bnpp_scope *a, const bnpp_scope *b, uint32_t *out_var_id, uint32_t *out_card);
+/* code/domain.cpp:15-26: product of the cardinalities; 0 on overflow of 2^64 */
+uint64_t bnpp_scope_size(const bnpp_scope *s);
+
+/* ---- the fused elimination step (K3; also the engine under every op below) ---- */
+/* out[o] = sum_{x < card(elim_var)}  prod_k  operand_k[ pi_k(o, x) ]
+ * Replaces `prod *= *pf` over a bucket followed by `prod.sum_out(var)`
+ * (code/model.cpp:414-418) without materialising the product.
+ *   elim_var  < 0 : no variable is summed out (pure k-ary product).
+ *   divide != 0   : k must be 2; computes operand_0 / operand_1 (code/factor.cpp:149-180);
+ *                   a zero divisor sets BNPP_STATUS_ZERO_DIVISOR.
+ * Every operand variable must be in `out` or be elim_var.  `out` is dense over
+ * out_scope, in ANY axis order the caller chooses. */
+int bnpp_product_sum_out(bnpp_ctx *ctx, int k, const bnpp_operand *operands,
+                         const bnpp_scope *out_scope, int64_t elim_var, int divide,
+                         double *out_dev, double *z_dev);
+
+/* ---- reference-shaped single ops ---------------------------------------------- */
+/* Factor::product / Factor::divide, code/factor.cpp:117-180. out is dense over
+ * bnpp_union_scope(a, b). */
+int bnpp_product(bnpp_ctx *ctx, const bnpp_scope *sa, const double *a_dev,
+                 const bnpp_scope *sb, const double *b_dev, int divide,
+                 double *out_dev, double *z_dev);
+/* Factor::sum_out, code/factor.cpp:182-212. out is dense over `s` minus var (order
+ * kept); if var is not in scope the table is copied (code/factor.cpp:185-188). */
+int bnpp_sum_out(bnpp_ctx *ctx, const bnpp_scope *s, const double *in_dev, uint32_t var,
+                 double *out_dev, double *z_dev);
+/* Factor::conditioning, code/factor.cpp:214-242. Observed variables (ev_var/ev_val
+ * pairs; ids not in scope are ignored) are pinned, free axes keep their order. */
+int bnpp_condition(bnpp_ctx *ctx, const bnpp_scope *s, const double *in_dev,
+                   int n_ev, const uint32_t *ev_var, const uint32_t *ev_val,
+                   double *out_dev, double *z_dev);
+/* Factor::normalize, code/factor.cpp:244-255: out[i] = in[i] / Z with TRUE division.
+ * Z is *z_dev when z_dev != NULL (device-resident, no sync) else z_host. */
+int bnpp_normalize(bnpp_ctx *ctx, uint64_t n, const double *in_dev, const double *z_dev, double z_host,
+                   double *out_dev);
+/* Factor::max (starts from 0.0), Factor::min (starts from the partition),
+ * code/factor.cpp:97-115, and the plain sum (`partition +=` lines).
+ * op: 0 = sum, 1 = max, 2 = min.  init is the min's start value. result_dev: device double. */
+int bnpp_reduce(bnpp_ctx *ctx, int op, uint64_t n, const double *in_dev, double init, double *result_dev);
+
+/* ---- factor-graph sum-product (K7), code/graph.cpp:256-403 --------------------- */
+typedef struct bnpp_fg bnpp_fg;
+/* Builds the device edge tables once.  Factor f has scope
+ * fscope[foff[f] .. foff[f+1]) and a dense table of host doubles at ftab + toff[f].
+ * Messages start uniform 1/card (code/graph.cpp:261-274). */
+int bnpp_fg_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfac,
+                   const int32_t *foff, const uint32_t *fscope,
+                   const uint64_t *toff, const double *ftab_host, bnpp_fg **out);
+int bnpp_fg_destroy(bnpp_fg *fg);
+/* One sweep = all variable->factor updates, then all factor->variable updates
+ * (code/graph.cpp:298-326); *maxerror_host receives the sweep's max relative change
+ * (NaN ignored, inf kept, code/graph.cpp:349-356).  Synchronises. */
+int bnpp_fg_sweep(bnpp_fg *fg, double *maxerror_host);
+/* FactorGraph::update(max, epsilon), code/graph.cpp:298-332: *sweeps receives the
+ * 0-based index of the converging sweep, or max_sweeps. */
+int bnpp_fg_update(bnpp_fg *fg, uint32_t max_sweeps, double epsilon, uint32_t *sweeps);
+/* FactorGraph::marginal for every variable (code/graph.cpp:393-403):
+ * out_host[moff_var[v] .. +card[v]) with moff_var the exclusive prefix sum of card. */
+int bnpp_fg_marginals(bnpp_fg *fg, double *out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNPP_B200_H_ */

@@ -1,0 +1,226 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against
+(1) per-op dumps of the unmodified reference (tests/golden/ops.json.gz) and
+(2) the CPU oracle on seeded inputs.  Values are BIT-EXACT (same multiplication and
+summation order as the reference); partitions (tree-reduced on the GPU, sequential in
+the reference) agree to 1e-12 relative."""
+import math
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle as orc  # noqa: E402
+
+ZREL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    from bnpp_b200 import capi
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device; there is no CPU fallback"
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def dev(ctx, rec, cards):
+    from bnpp_b200.factor import DeviceFactor
+    return DeviceFactor.from_host(ctx, rec["scope"], [cards[v] for v in rec["scope"]], rec["values"], rec["partition"])
+
+
+def zclose(a, b):
+    return a == b or math.isclose(a, b, rel_tol=ZREL, abs_tol=1e-300)
+
+
+def test_reference_op_dumps(ctx, golden_ops):
+    """product / divide / sum_out / conditioning / normalize / max / min, code/factor.cpp:97-255"""
+    for c in golden_ops:
+        cards = c["cards"]
+        a, b = dev(ctx, c["a"], cards), dev(ctx, c["b"], cards)
+        p = a.product(b)
+        assert p.scope == c["p"]["scope"]
+        assert np.array_equal(p.values(), np.array(c["p"]["values"]))
+        assert zclose(p.partition, c["p"]["partition"])
+        q = a.divide(b)
+        assert q.scope == c["q"]["scope"] and np.array_equal(q.values(), np.array(c["q"]["values"]))
+        assert zclose(q.partition, c["q"]["partition"])
+        assert ctx.status() == 0
+        s = p.sum_out(c["sum_var"])
+        assert s.scope == c["s"]["scope"] and np.array_equal(s.values(), np.array(c["s"]["values"]))
+        assert zclose(s.partition, c["s"]["partition"])
+        ev = {int(k): v for k, v in c["evidence"].items()}
+        cf = p.condition(ev)
+        assert cf.scope == c["c"]["scope"] and np.array_equal(cf.values(), np.array(c["c"]["values"]))
+        assert zclose(cf.partition, c["c"]["partition"])
+        # the reference normalises with ITS sequential partition; feed the same Z for a bit-exact check
+        pref = dev(ctx, c["p"], cards)
+        n = pref.normalize()
+        assert np.array_equal(n.values(), np.array(c["n"]["values"])) and n.partition == 1.0
+        assert pref.max() == c["max_p"] and pref.min() == c["min_p"]
+        qref = dev(ctx, c["q"], cards)
+        assert qref.max() == c["max_q"] and qref.min() == c["min_q"]
+
+
+def test_zero_divisor_flag(ctx):
+    from bnpp_b200.factor import DeviceFactor
+    a = DeviceFactor.from_host(ctx, [0, 1], [2, 2], [1, 2, 3, 4])
+    b = DeviceFactor.from_host(ctx, [1], [2], [0.0, 2.0])
+    a.divide(b)
+    assert ctx.status() & 1          # the reference asserts here (code/factor.cpp:169)
+    assert ctx.status() == 0         # cleared
+
+
+def rand_factor(ctx, rng, scope, cards):
+    from bnpp_b200.factor import DeviceFactor
+    n = int(np.prod([cards[v] for v in scope])) if scope else 1
+    vals = np.random.default_rng(rng.randrange(1 << 30)).uniform(0.1, 1.0, n)
+    of = orc.OFactor(scope, vals)
+    return of, DeviceFactor.from_host(ctx, scope, [cards[v] for v in scope], vals, of.partition)
+
+
+@pytest.mark.parametrize("binary", [True, False])
+def test_fused_step_random(ctx, binary):
+    """k-ary product -> sum_out in one kernel (code/model.cpp:414-418) on random scopes,
+    random output axis orders, with and without an eliminated variable: bit-exact vs the oracle."""
+    from bnpp_b200.factor import fused_product_sum_out
+    rng = random.Random(7 if binary else 11)
+    for case in range(120):
+        nvars = rng.randint(1, 12 if binary else 7)
+        cards = [2] * nvars if binary else [rng.choice([2, 2, 3, 4, 5]) for _ in range(nvars)]
+        k = rng.randint(1, 6)
+        ofs, dfs = [], []
+        for _ in range(k):
+            w = rng.randint(0, nvars)
+            sc = rng.sample(range(nvars), w)
+            o, d = rand_factor(ctx, rng, sc, cards)
+            ofs.append(o); dfs.append(d)
+        union = []
+        for o in ofs:
+            union += [v for v in o.scope if v not in union]
+        elim = rng.choice(union) if union and rng.random() < 0.8 else None
+        out_scope = [v for v in union if v != elim]
+        rng.shuffle(out_scope)
+        want = orc.product_sum_out(ofs, out_scope, elim, cards)
+        got = fused_product_sum_out(ctx, dfs, out_scope, elim)
+        assert np.array_equal(got.values(), want.values), (case, ctx.last_launch())
+        assert zclose(got.partition, want.partition)
+
+
+def headline_case(kind, nbits, k, reverse_b):
+    """SURVEY §8d headline shapes at `nbits` union bits: returns (scopeA, scopeB, elim var)"""
+    allv = list(range(nbits))
+    if kind == "elem":
+        a, b = allv, list(allv)
+    elif kind == "bcast":
+        a, b = allv[:-1], allv[1:]
+    else:  # small: B over 10 scattered variables
+        step = max(1, nbits // 10)
+        a, b = allv, allv[::step][:10]
+        if k not in b:
+            b = sorted(set(b[:-1] + [k]))
+    if reverse_b:
+        b = b[::-1]
+    return a, b, k
+
+
+@pytest.mark.parametrize("kind", ["elem", "bcast", "small"])
+@pytest.mark.parametrize("reverse_b", [False, True])
+def test_headline_shapes_reduced(ctx, kind, reverse_b):
+    """F-elem / F-bcast / F-small x sum-out position {leading, middle, trailing}, 2^20 union entries,
+    entry-wise against the oracle"""
+    from bnpp_b200.factor import fused_product_sum_out
+    nbits = 20
+    rng = random.Random(3)
+    cards = [2] * nbits
+    for k in (0, nbits // 2, nbits - 1):
+        sa, sb, elim = headline_case(kind, nbits, k, reverse_b)
+        if elim not in sa and elim not in sb:
+            continue
+        oa, da = rand_factor(ctx, rng, sa, cards)
+        ob, db = rand_factor(ctx, rng, sb, cards)
+        union = sa + [v for v in sb if v not in sa]
+        out_scope = [v for v in union if v != elim]
+        want = orc.product_sum_out([oa, ob], out_scope, elim, cards)
+        got = fused_product_sum_out(ctx, [da, db], out_scope, elim)
+        assert np.array_equal(got.values(), want.values), (kind, k, reverse_b, ctx.last_launch())
+        assert zclose(got.partition, want.partition)
+
+
+def test_mixed_cardinality_large(ctx):
+    from bnpp_b200.factor import fused_product_sum_out
+    rng = random.Random(5)
+    cards = [3, 4, 5, 2, 3, 4, 2, 5, 3, 2, 4]      # 1.7M union entries
+    sa = [0, 1, 2, 3, 4, 5, 6, 7]
+    sb = [10, 9, 8, 7, 2, 0]
+    oa, da = rand_factor(ctx, rng, sa, cards)
+    ob, db = rand_factor(ctx, rng, sb, cards)
+    for elim in (0, 7, 10, 2):
+        union = sa + [v for v in sb if v not in sa]
+        out_scope = [v for v in union if v != elim]
+        want = orc.product_sum_out([oa, ob], out_scope, elim, cards)
+        got = fused_product_sum_out(ctx, [da, db], out_scope, elim)
+        assert np.array_equal(got.values(), want.values)
+        assert zclose(got.partition, want.partition)
+
+
+def test_edge_cases(ctx):
+    """width-0 operands, size-1 outputs, variable not in scope, everything observed"""
+    from bnpp_b200.factor import DeviceFactor
+    s = DeviceFactor.from_host(ctx, [], [], [2.5])
+    a = DeviceFactor.from_host(ctx, [4, 2], [3, 2], [1, 2, 3, 4, 5, 6])
+    p = s.product(a)
+    assert p.scope == [4, 2] and np.array_equal(p.values(), 2.5 * np.arange(1, 7)) and p.partition == 52.5
+    p2 = a.product(s)
+    assert np.array_equal(p2.values(), p.values())
+    ss = s.product(s)
+    assert ss.scope == [] and ss.values()[0] == 6.25 and ss.partition == 6.25
+    c = a.sum_out(9)                       # not in scope: deep copy (code/factor.cpp:185-188)
+    assert c.scope == [4, 2] and np.array_equal(c.values(), a.values()) and c.partition == a.partition
+    t = a.sum_out(4).sum_out(2)
+    assert t.scope == [] and t.values()[0] == 21.0 and t.partition == 21.0
+    e = a.condition({4: 2, 2: 1, 7: 0})     # all observed -> width-0 scalar
+    assert e.scope == [] and e.values()[0] == 6.0 and e.partition == 6.0
+    e2 = a.condition({})
+    assert np.array_equal(e2.values(), a.values())
+    n = DeviceFactor.from_host(ctx, [1], [2], [0.0, 0.0]).normalize()
+    assert np.all(np.isnan(n.values()))    # 0/0, true division as in code/factor.cpp:250
+
+
+def test_errors(ctx):
+    from bnpp_b200 import capi
+    from bnpp_b200.factor import DeviceFactor
+    a = DeviceFactor.from_host(ctx, [0, 1], [2, 2], [1, 2, 3, 4])
+    out = DeviceFactor.empty(ctx, [0], [2])
+    with pytest.raises(capi.BnppError) as ei:   # variable 1 neither kept nor eliminated
+        ctx.product_sum_out([(a.ptr, a.scope, a.cards, None)], [0], [2], None, out.ptr)
+    assert ei.value.code == -1
+    with pytest.raises(capi.BnppError):          # cardinality mismatch
+        ctx.product_sum_out([(a.ptr, a.scope, a.cards, None)], [0], [3], 1, out.ptr)
+
+
+def test_sum_out_commutes_and_partition_invariant_2p26(ctx):
+    """size-independent properties on a table too big to check entry-wise against the CPU oracle"""
+    import torch
+    from bnpp_b200.factor import DeviceFactor, fused_product_sum_out
+    nbits = 26
+    g = torch.Generator(device="cuda").manual_seed(1)
+    scope = list(range(nbits))
+    a = DeviceFactor.empty(ctx, scope, [2] * nbits)
+    b = DeviceFactor.empty(ctx, scope[1:], [2] * (nbits - 1))
+    a.buf[:-1] = torch.rand(a.size, generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+    b.buf[:-1] = torch.rand(b.size, generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+    torch.cuda.synchronize()
+    zs = []
+    for k in (0, 13, 25):
+        out = fused_product_sum_out(ctx, [a, b], [v for v in scope if v != k], k)
+        zs.append(out.partition)
+        assert zclose(out.sum(), out.partition)
+    assert all(math.isclose(z, zs[0], rel_tol=1e-12) for z in zs)     # Z(sum_out) = Z(product), any variable
+    want = float((a.buf[:-1].view(2, -1) * b.buf[:-1]).sum().item())
+    assert math.isclose(zs[0], want, rel_tol=1e-11)
+    s1 = a.sum_out(3).sum_out(20)
+    s2 = a.sum_out(20).sum_out(3)
+    assert torch.allclose(s1.buf[:-1], s2.buf[:-1], rtol=1e-14, atol=0.0)   # (p+q)+(r+s) vs (p+r)+(q+s)

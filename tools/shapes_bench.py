@@ -1,0 +1,105 @@
+#!/usr/bin/env python
+"""Times the fused product+sum-out kernel on the SURVEY §8d headline shapes
+(F-elem / F-bcast / F-small x sum-out position x B order) and prints achieved GB/s of
+ALGORITHMIC bytes 8*(#A + #B + #out) against the measured HBM peak.
+
+    python tools/shapes_bench.py [--bits 28] [--iters 5] [--json out.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from bnpp_b200 import capi  # noqa: E402
+from bnpp_b200.factor import DeviceFactor  # noqa: E402
+
+
+def peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def shapes(nbits):
+    allv = list(range(nbits))
+    small = allv[:: max(1, nbits // 10)][:10]
+    out = []
+    for kind, a, b in (("elem", allv, allv), ("bcast", allv[:-1], allv[1:]), ("small", allv, small)):
+        for k in (0, nbits // 2, nbits - 1):
+            for rev in (False, True):
+                bb = list(b)
+                if kind == "small" and k not in bb:
+                    bb = sorted(set(bb[:-1] + [k]))
+                if k not in a and k not in bb:
+                    continue
+                if rev:
+                    bb = bb[::-1]
+                out.append((kind, k, rev, list(a), bb))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bits", type=int, default=28)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--only", default=None, help="kind filter")
+    ap.add_argument("--no-reverse", action="store_true")
+    args = ap.parse_args()
+    ctx = capi.Context(0)
+    peak, how = peak_gbs()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    cache = {}
+
+    def table(scope):
+        key = len(scope)
+        if key not in cache:
+            f = DeviceFactor.empty(ctx, list(range(key)), [2] * key)
+            f.buf[:-1] = torch.rand(f.size, generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+            cache[key] = f
+        return cache[key]
+
+    rows = []
+    for kind, k, rev, sa, sb in shapes(args.bits):
+        if args.only and kind != args.only:
+            continue
+        if rev and args.no_reverse:
+            continue
+        A, B = table(sa), table(sb)
+        union = sa + [v for v in sb if v not in sa]
+        out_scope = [v for v in union if v != k]
+        out = DeviceFactor.empty(ctx, out_scope, [2] * len(out_scope))
+        ops = [(A.ptr, sa, [2] * len(sa), None), (B.ptr, sb, [2] * len(sb), None)]
+        torch.cuda.synchronize()
+        s = ctx.torch_stream
+        times = []
+        for it in range(args.iters + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            ctx.product_sum_out(ops, out_scope, [2] * len(out_scope), k, out.ptr, out.zptr)
+            e1.record(s)
+            e1.synchronize()
+            if it >= 2:
+                times.append(e0.elapsed_time(e1))
+        ms = sum(times) / len(times)
+        nbytes = 8 * (A.size + B.size + out.size)
+        gbs = nbytes / ms / 1e6
+        entries = 2 ** len(union)
+        row = {"kind": kind, "k": k, "reverse_b": rev, "union_bits": len(union), "ms": ms, "GBs": gbs,
+               "frac": gbs / peak, "entries_per_s": entries / ms * 1e3, "kernel": ctx.last_launch()[0]}
+        rows.append(row)
+        print("%-6s k=%2d rev=%d  %8.3f ms  %8.1f GB/s  %5.1f%% of %s peak  %.3e entries/s  %s"
+              % (kind, k, rev, ms, gbs, 100 * gbs / peak, how, row["entries_per_s"], row["kernel"]), flush=True)
+        del out
+    if args.json:
+        json.dump({"peak_gbs": peak, "peak_kind": how, "rows": rows}, open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
