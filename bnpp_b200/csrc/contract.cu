@@ -10,12 +10,20 @@
 // Where the reference walks an odometer and does two hash lookups per scope variable
 // per entry (code/domain.cpp:113-123,162-179), the plan below turns every operand
 // into a stride vector over the OUTPUT's axes (stride 0 = axis absent = broadcast,
-// SURVEY A.1), merges axes that are contiguous in every operand, and the kernel
-// recovers the mixed-radix digits of its linear index with multiply-high divisions.
-// Each thread owns a [V x C] micro-tile: V (1 or 2) consecutive output entries times the
-// C values of the eliminated variable, loaded with 128/256-bit accesses whenever the
-// operand's layout makes them contiguous.  HBM-bound: algorithmic bytes per launch =
-// 8 * (sum_k #F_k + #out)   (SURVEY §8d).
+// SURVEY A.1) and the kernel recovers operand offsets from its linear item index:
+//   * all extents powers of two (binary variables: every BASELINE config): offsets are
+//     sums of bit-fields of the index, merged per operand;
+//   * otherwise: mixed-radix digits by multiply-high division over merged axes.
+// The ITERATION order is chosen by the plan, not dictated by the output layout: above a
+// tile of the output's fastest axes, axes that a large operand lacks are iterated
+// fastest, so that operand's tile is re-read from L2 instead of HBM.
+// Each thread owns U items; an item is a [V x C] micro-tile: V (1 or 2) consecutive
+// output entries times the C values of the eliminated variable, loaded with 128/256-bit
+// accesses whenever the operand's layout makes them contiguous.  HBM-bound: algorithmic
+// bytes per launch = 8 * (sum_k #F_k + #out)   (SURVEY §8d).
+//
+// Arithmetic is written with __dmul_rn/__dadd_rn (no FMA contraction) so every entry is
+// bit-identical to the reference's `((1*f1)*f2)*...` then `0 + p(x=0) + p(x=1) + ...`.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -25,18 +33,23 @@
 
 namespace bnpp {
 
+// How the [V x C] micro-tile of one operand sits in memory.  A class fixes the LOADS
+// (issued for all operands of all U items before anything consumes them) and the
+// index map used later to pick micro-tile element (j, x) out of the loaded registers.
 enum LoadClass : uint8_t {
-    LC_SCALAR = 0,  // V*C independent 8-byte loads (duplicates skipped when a stride is 0)
-    LC_BCAST,       // one value for the whole micro-tile
-    LC_VX,          // x contiguous (stride 1, C == 2): one 16-byte load per output entry
-    LC_VX_B,        //   ... and the operand does not depend on the innermost output axis
-    LC_VL,          // innermost output axis contiguous (V == 2): one 16-byte load per x
-    LC_VL_B,        //   ... and the operand does not depend on x
-    LC_V4,          // [j][x] contiguous: one 32-byte load, element 2*j + x
-    LC_V4T,         // [x][j] contiguous: one 32-byte load, element 2*x + j
+    LC_BCAST = 0,   // one 8-byte load, same value for the whole micro-tile
+    LC_VX,          // x contiguous (stride 1, C == 2): a 16-byte load per output entry      -> r[2j+x]
+    LC_VX_B,        //   ... operand does not depend on the innermost output axis             -> r[x]
+    LC_VL,          // innermost output axis contiguous (V == 2): a 16-byte load per x         -> r[2x+j]
+    LC_VL_B,        //   ... operand does not depend on x                                     -> r[j]
+    LC_V4,          // [j][x] contiguous: one 32-byte load                                    -> r[2j+x]
+    LC_V4T,         // [x][j] contiguous: one 32-byte load                                    -> r[2x+j]
+    LC_S_X,         // two 8-byte loads along x                                               -> r[x]
+    LC_S_L,         // two 8-byte loads along the innermost output axis                       -> r[j]
+    LC_S_JX,        // four 8-byte loads                                                      -> r[2j+x]
 };
 
-struct ContractParams {
+struct ParamsHead {
     const double *in[kMaxK];
     double *out;
     double *partials;
@@ -44,19 +57,38 @@ struct ContractParams {
     double *z;
     unsigned int *status;
     uint64_t n_items;           // output entries / V
-    uint32_t R;                 // iteration axes, outermost first
     uint32_t cx;                // cardinality of the eliminated variable (1 = none)
-    FastDiv div[kMaxR];
-    uint32_t so[kMaxR];         // output stride per axis (elements, per item on the last axis)
-    uint32_t s[kMaxK][kMaxR];   // operand stride per axis
     uint32_t sx[kMaxK];         // operand stride of the eliminated variable
     uint32_t sl[kMaxK];         // operand stride between the V entries of an item
+    uint32_t sol;               // output stride between the V entries of an item
     uint8_t cls[kMaxK];
     uint8_t out_vec;            // 16-byte store allowed
 };
 
+// Mixed-radix iteration space: digits by multiply-high division, outermost axis first.
+struct ParamsMR {
+    ParamsHead h;
+    uint32_t R;
+    FastDiv div[kMaxR];
+    uint32_t so[kMaxR];         // output stride per axis (per item on the innermost axis)
+    uint32_t s[kMaxK][kMaxR];   // operand stride per axis
+};
+
+// Power-of-two iteration space: off = sum_f ((item >> sh) & mask) * mul, fields merged PER
+// OPERAND, so an operand laid out like the output costs one field no matter how
+// scattered the other operands' axes are.
+constexpr int kMaxF = 24;
+struct Field {
+    uint32_t mask, mul, sh;
+};
+struct ParamsP2 {
+    ParamsHead h;
+    uint8_t nf[kMaxK + 1];      // [K] is the output
+    Field f[kMaxK + 1][kMaxF];
+};
+
 template <int K>
-__device__ __forceinline__ void decompose(const ContractParams &p, uint32_t item, uint32_t (&off)[K], uint32_t &ooff)
+__device__ __forceinline__ void decompose(const ParamsMR &p, uint32_t item, uint32_t (&off)[K], uint32_t &ooff)
 {
 #pragma unroll
     for (int k = 0; k < K; ++k) off[k] = 0;
@@ -77,192 +109,211 @@ __device__ __forceinline__ void decompose(const ContractParams &p, uint32_t item
     }
 }
 
-template <int C, int V>
-__device__ __forceinline__ void load_tile(const double *__restrict__ base, uint32_t off, uint32_t sx, uint32_t sl,
-                                          uint8_t cls, double (&t)[V][C])
+template <int K>
+__device__ __forceinline__ void decompose(const ParamsP2 &p, uint32_t item, uint32_t (&off)[K], uint32_t &ooff)
 {
-    const double *p = base + off;
-    switch (cls) {
-    case LC_BCAST: {
-        const double v = ld1(p);
 #pragma unroll
-        for (int j = 0; j < V; ++j)
-#pragma unroll
-            for (int x = 0; x < C; ++x) t[j][x] = v;
-        break;
+    for (int k = 0; k < K; ++k) {
+        uint32_t o = 0;
+        for (int f = 0; f < (int)p.nf[k]; ++f) o += ((item >> p.f[k][f].sh) & p.f[k][f].mask) * p.f[k][f].mul;
+        off[k] = o;
     }
-    case LC_VX:
-        if (C == 2) {
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const double2 v = ld2(p + j * sl);
-                t[j][0] = v.x;
-                t[j][C - 1] = v.y;
-            }
-        }
+    uint32_t o = 0;
+    for (int f = 0; f < (int)p.nf[K]; ++f) o += ((item >> p.f[K][f].sh) & p.f[K][f].mask) * p.f[K][f].mul;
+    ooff = o;
+}
+
+template <int C, int V>
+__device__ __forceinline__ void issue_loads(const double *__restrict__ p, uint32_t sx, uint32_t sl, uint8_t cls,
+                                            double (&r)[4])
+{
+    switch (cls) {
+    case LC_BCAST:
+        r[0] = ld1(p);
         break;
     case LC_VX_B:
-        if (C == 2) {
-            const double2 v = ld2(p);
+    case LC_VL_B: {
+        const double2 a = ld2(p);
+        r[0] = a.x; r[1] = a.y;
+        break;
+    }
+    case LC_VX: {
+        const double2 a = ld2(p), b = ld2(p + sl);
+        r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
+        break;
+    }
+    case LC_VL: {
+        const double2 a = ld2(p), b = ld2(p + sx);
+        r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
+        break;
+    }
+    case LC_V4:
+    case LC_V4T: {
+        const double4_t a = ld4(p);
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+        break;
+    }
+    case LC_S_X:
+        r[0] = ld1(p); r[1] = ld1(p + sx);
+        break;
+    case LC_S_L:
+        r[0] = ld1(p); r[1] = ld1(p + sl);
+        break;
+    default:
+        r[0] = ld1(p); r[1] = ld1(p + sx); r[2] = ld1(p + sl); r[3] = ld1(p + sl + sx);
+        break;
+    }
+}
+
+// element (j, x) of the micro-tile; j and x are compile-time, cls is grid-uniform
+__device__ __forceinline__ double pick(const double (&r)[4], uint8_t cls, int j, int x)
+{
+    switch (cls) {
+    case LC_BCAST: return r[0];
+    case LC_VX_B:
+    case LC_S_X: return r[x];
+    case LC_VL_B:
+    case LC_S_L: return r[j];
+    case LC_VL:
+    case LC_V4T: return r[2 * x + j];
+    default: return r[2 * j + x];
+    }
+}
+
+// Fast path: eliminated variable binary (C = 2) or absent (C = 1).  Each CTA walks
+// chunks of U * kBlock consecutive items.  Phase 1 issues the loads of all K operands of
+// all U items of a thread back to back; nothing reads a loaded register until phase 2,
+// so U * K requests per thread are in flight -- that, not occupancy, is what feeds HBM.
+template <class P, int K, int C, int V, int U, bool DIV>
+__global__ void __launch_bounds__(kBlock) contract_fast(const __grid_constant__ P p)
+{
+    const ParamsHead &h = p.h;
+    const uint64_t chunk = (uint64_t)U * kBlock;
+    const uint64_t step = (uint64_t)gridDim.x * chunk;
+    const uint64_t last = h.n_items - 1;
+    double zacc = 0.0;
+    bool zero_div = false;
+    for (uint64_t base = (uint64_t)blockIdx.x * chunk + threadIdx.x; base < h.n_items; base += step) {
+        double raw[U][K][4];
+        uint32_t ooff[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint64_t it = base + (uint64_t)u * kBlock;
+            uint32_t off[K];
+            decompose<K>(p, (uint32_t)(it < last ? it : last), off, ooff[u]);   // tail items clamp, their result is dropped
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) raw[u][k][e] = 0.0;
+                issue_loads<C, V>(h.in[k] + off[k], h.sx[k], h.sl[k], h.cls[k], raw[u][k]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double r[V];
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-                t[j][0] = v.x;
-                t[j][C - 1] = v.y;
-            }
-        }
-        break;
-    case LC_VL:
-        if (V == 2) {
-#pragma unroll
-            for (int x = 0; x < C; ++x) {
-                const double2 v = ld2(p + x * sx);
-                t[0][x] = v.x;
-                t[V - 1][x] = v.y;
-            }
-        }
-        break;
-    case LC_VL_B:
-        if (V == 2) {
-            const double2 v = ld2(p);
-#pragma unroll
-            for (int x = 0; x < C; ++x) {
-                t[0][x] = v.x;
-                t[V - 1][x] = v.y;
-            }
-        }
-        break;
-    case LC_V4:
-        if (V == 2 && C == 2) {
-            const double4_t v = ld4(p);
-            t[0][0] = v.x; t[0][C - 1] = v.y; t[V - 1][0] = v.z; t[V - 1][C - 1] = v.w;
-        }
-        break;
-    case LC_V4T:
-        if (V == 2 && C == 2) {
-            const double4_t v = ld4(p);
-            t[0][0] = v.x; t[V - 1][0] = v.y; t[0][C - 1] = v.z; t[V - 1][C - 1] = v.w;
-        }
-        break;
-    default: {
-#pragma unroll
-        for (int j = 0; j < V; ++j)
-#pragma unroll
-            for (int x = 0; x < C; ++x) {
-                if (x > 0 && sx == 0) t[j][x] = t[j][0];
-                else if (j > 0 && sl == 0) t[j][x] = t[0][x];
-                else t[j][x] = ld1(p + j * sl + x * sx);
-            }
-    }
-    }
-}
-
-// Fast path: eliminated variable binary (C = 2) or absent (C = 1).
-template <int K, int C, int V, bool DIV>
-__global__ void __launch_bounds__(kBlock) contract_fast(const __grid_constant__ ContractParams p)
-{
-    const uint64_t step = (uint64_t)gridDim.x * kBlock;
-    double zacc = 0.0;
-    bool zero_div = false;
-    for (uint64_t it = (uint64_t)blockIdx.x * kBlock + threadIdx.x; it < p.n_items; it += step) {
-        uint32_t off[K], ooff;
-        decompose<K>(p, (uint32_t)it, off, ooff);
-        double acc[V][C];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            double t[V][C];
-            load_tile<C, V>(p.in[k], off[k], p.sx[k], p.sl[k], p.cls[k], t);
-#pragma unroll
-            for (int j = 0; j < V; ++j)
 #pragma unroll
                 for (int x = 0; x < C; ++x) {
-                    if (k == 0) acc[j][x] = t[j][x];
-                    else if (DIV) { zero_div |= (t[j][x] == 0.0); acc[j][x] = acc[j][x] / t[j][x]; }
-                    else acc[j][x] = acc[j][x] * t[j][x];
+                    double a = pick(raw[u][0], h.cls[0], j, x);
+#pragma unroll
+                    for (int k = 1; k < K; ++k) {
+                        const double t = pick(raw[u][k], h.cls[k], j, x);
+                        if (DIV) { zero_div |= (t == 0.0); a = __ddiv_rn(a, t); }
+                        else a = __dmul_rn(a, t);
+                    }
+                    r[j] = (x == 0) ? a : __dadd_rn(r[j], a);
                 }
-        }
-        double r[V];
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            r[j] = acc[j][0];
-#pragma unroll
-            for (int x = 1; x < C; ++x) r[j] += acc[j][x];
-            zacc += r[j];
-        }
-        double *o = p.out + ooff;
-        if (V == 2) {
-            if (p.out_vec) *reinterpret_cast<double2 *>(o) = make_double2(r[0], r[V - 1]);
-            else { o[0] = r[0]; o[1] = r[V - 1]; }
-        } else {
-            o[0] = r[0];
+            }
+            if (base + (uint64_t)u * kBlock > last) continue;
+            double *o = h.out + ooff[u];
+            if (V == 2) {
+                zacc = __dadd_rn(zacc, __dadd_rn(r[0], r[V - 1]));
+                if (h.out_vec) *reinterpret_cast<double2 *>(o) = make_double2(r[0], r[V - 1]);
+                else { o[0] = r[0]; o[h.sol] = r[V - 1]; }
+            } else {
+                zacc = __dadd_rn(zacc, r[0]);
+                o[0] = r[0];
+            }
         }
     }
-    if (DIV && zero_div) atomicOr(p.status, BNPP_STATUS_ZERO_DIVISOR);
-    grid_sum_to(zacc, p.partials, p.ticket, p.z);
+    if (DIV && zero_div) atomicOr(h.status, BNPP_STATUS_ZERO_DIVISOR);
+    grid_sum_to(zacc, h.partials, h.ticket, h.z);
 }
 
-// Generic path: any cardinality of the eliminated variable, one output entry per thread.
-template <int K, bool DIV>
-__global__ void __launch_bounds__(kBlock) contract_generic(const __grid_constant__ ContractParams p)
+// Generic path: any cardinality of the eliminated variable, one output entry per item.
+template <class P, int K, bool DIV>
+__global__ void __launch_bounds__(kBlock) contract_generic(const __grid_constant__ P p)
 {
+    const ParamsHead &h = p.h;
     const uint64_t step = (uint64_t)gridDim.x * kBlock;
     double zacc = 0.0;
     bool zero_div = false;
-    for (uint64_t it = (uint64_t)blockIdx.x * kBlock + threadIdx.x; it < p.n_items; it += step) {
+    for (uint64_t it = (uint64_t)blockIdx.x * kBlock + threadIdx.x; it < h.n_items; it += step) {
         uint32_t off[K], ooff;
         decompose<K>(p, (uint32_t)it, off, ooff);
         double acc = 0.0;
-        for (uint32_t x = 0; x < p.cx; ++x) {
-            double v = ld1(p.in[0] + off[0] + x * p.sx[0]);
+        for (uint32_t x = 0; x < h.cx; ++x) {
+            double v = ld1(h.in[0] + off[0] + x * h.sx[0]);
 #pragma unroll
             for (int k = 1; k < K; ++k) {
-                const double t = ld1(p.in[k] + off[k] + x * p.sx[k]);
-                if (DIV) { zero_div |= (t == 0.0); v = v / t; }
-                else v = v * t;
+                const double t = ld1(h.in[k] + off[k] + x * h.sx[k]);
+                if (DIV) { zero_div |= (t == 0.0); v = __ddiv_rn(v, t); }
+                else v = __dmul_rn(v, t);
             }
-            acc += v;
+            acc = __dadd_rn(acc, v);
         }
-        p.out[ooff] = acc;
-        zacc += acc;
+        h.out[ooff] = acc;
+        zacc = __dadd_rn(zacc, acc);
     }
-    if (DIV && zero_div) atomicOr(p.status, BNPP_STATUS_ZERO_DIVISOR);
-    grid_sum_to(zacc, p.partials, p.ticket, p.z);
+    if (DIV && zero_div) atomicOr(h.status, BNPP_STATUS_ZERO_DIVISOR);
+    grid_sum_to(zacc, h.partials, h.ticket, h.z);
 }
 
-typedef void (*kernel_fn)(const ContractParams);
+// ---------------------------------------------------------------------------
+// kernel selection
+// ---------------------------------------------------------------------------
+template <class P>
+struct Launch {
+    typedef void (*fn_t)(const P);
 
-template <int K>
-static kernel_fn pick_fast(int C, int V)
-{
-    if (C == 1) return V == 2 ? contract_fast<K, 1, 2, false> : contract_fast<K, 1, 1, false>;
-    return V == 2 ? contract_fast<K, 2, 2, false> : contract_fast<K, 2, 1, false>;
-}
+    template <int K, int U>
+    static fn_t fast(int C, int V)
+    {
+        if (C == 1) return V == 2 ? contract_fast<P, K, 1, 2, U, false> : contract_fast<P, K, 1, 1, U, false>;
+        return V == 2 ? contract_fast<P, K, 2, 2, U, false> : contract_fast<P, K, 2, 1, U, false>;
+    }
 
-static kernel_fn pick(int K, int C, int V, bool div, bool generic)
-{
-    if (generic) {
-        if (div) return contract_generic<2, true>;
+    static fn_t pick(int K, int C, int V, bool div, bool generic, int &U)
+    {
+        U = 1;
+        if (generic) {
+            if (div) return contract_generic<P, 2, true>;
+            switch (K) {
+            case 1: return contract_generic<P, 1, false>;
+            case 2: return contract_generic<P, 2, false>;
+            case 3: return contract_generic<P, 3, false>;
+            case 4: return contract_generic<P, 4, false>;
+            case 5: return contract_generic<P, 5, false>;
+            default: return contract_generic<P, 6, false>;
+            }
+        }
+        if (div) {
+            U = 2;
+            if (C == 1) return V == 2 ? contract_fast<P, 2, 1, 2, 2, true> : contract_fast<P, 2, 1, 1, 2, true>;
+            return V == 2 ? contract_fast<P, 2, 2, 2, 2, true> : contract_fast<P, 2, 2, 1, 2, true>;
+        }
+        // U: items in flight per thread -- fewer operands => fewer bytes per item => more items
         switch (K) {
-        case 1: return contract_generic<1, false>;
-        case 2: return contract_generic<2, false>;
-        case 3: return contract_generic<3, false>;
-        case 4: return contract_generic<4, false>;
-        case 5: return contract_generic<5, false>;
-        default: return contract_generic<6, false>;
+        case 1: U = 4; return fast<1, 4>(C, V);
+        case 2: U = 2; return fast<2, 2>(C, V);
+        case 3: U = 2; return fast<3, 2>(C, V);
+        case 4: U = 1; return fast<4, 1>(C, V);
+        case 5: U = 1; return fast<5, 1>(C, V);
+        default: U = 1; return fast<6, 1>(C, V);
         }
     }
-    if (div) {
-        if (C == 1) return V == 2 ? contract_fast<2, 1, 2, true> : contract_fast<2, 1, 1, true>;
-        return V == 2 ? contract_fast<2, 2, 2, true> : contract_fast<2, 2, 1, true>;
-    }
-    switch (K) {
-    case 1: return pick_fast<1>(C, V);
-    case 2: return pick_fast<2>(C, V);
-    case 3: return pick_fast<3>(C, V);
-    case 4: return pick_fast<4>(C, V);
-    case 5: return pick_fast<5>(C, V);
-    default: return pick_fast<6>(C, V);
-    }
-}
+};
 
 // ---------------------------------------------------------------------------
 // host-side plan
@@ -271,9 +322,37 @@ struct Axis {
     uint32_t ext;
     uint64_t so;
     uint64_t s[kMaxK];
+    uint64_t miss;   // bytes of large operands that do NOT depend on this axis
 };
 
 static bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+static bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+static uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << l) < v) ++l; return l; }
+
+constexpr uint64_t kTileOutputs = 1u << 13;     // the output's fastest axes covering this many entries keep their order
+constexpr uint64_t kReuseBytes = 32ull << 20;   // operands above this do not survive in L2 between passes
+
+template <class P>
+static int launch(bnpp_ctx *ctx, P &p, int k, int C, int V, bool div, bool generic, const char *mode, uint32_t R)
+{
+    int U = 1;
+    typename Launch<P>::fn_t fn = Launch<P>::pick(k, C, V, div, generic, U);
+    uint64_t blocks = (p.h.n_items + (uint64_t)kBlock * U - 1) / ((uint64_t)kBlock * U);
+    const uint64_t cap = (uint64_t)ctx->sm_count * 8;   // persistent grid: up to 8 CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    fn<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(p);
+    BNPP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    char nm[128];
+    if (generic) snprintf(nm, sizeof nm, "contract_generic<%s,K=%d,div=%d> cx=%u R=%u", mode, k, div, p.h.cx, R);
+    else snprintf(nm, sizeof nm, "contract_fast<%s,K=%d,C=%d,V=%d,U=%d,div=%d> R=%u cls=%d,%d,%d", mode, k, C, V, U, div, R,
+                  p.h.cls[0], k > 1 ? p.h.cls[1] : -1, k > 2 ? p.h.cls[2] : -1);
+    ctx->last_kernel = nm;
+    ctx->last_grid = (uint32_t)blocks;
+    ctx->last_block = kBlock;
+    return BNPP_OK;
+}
 
 int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope,
              int64_t elim_var, int divide, double *out_dev, double *z_dev)
@@ -290,16 +369,20 @@ int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *ou
     uint64_t n_out = 1;
     for (int i = wr - 1; i >= 0; --i) {
         if (out_scope->card[i] == 0) return fail(ctx, BNPP_EINVAL, "zero cardinality");
+        if (elim_var >= 0 && out_scope->var_id[i] == (uint64_t)elim_var)
+            return fail(ctx, BNPP_EINVAL, "the eliminated variable is in the output scope");
         for (int j = i + 1; j < wr; ++j)
             if (out_scope->var_id[i] == out_scope->var_id[j]) return fail(ctx, BNPP_EINVAL, "duplicate variable in output scope");
         axes[i].ext = out_scope->card[i];
         axes[i].so = n_out;
+        axes[i].miss = 0;
         for (int q = 0; q < kMaxK; ++q) axes[i].s[q] = 0;
         n_out *= out_scope->card[i];
         if (n_out >= (1ull << 32)) return fail(ctx, BNPP_ETOOBIG, "output table has >= 2^32 entries");
     }
 
     uint64_t sx[kMaxK] = {0};
+    uint64_t op_bytes[kMaxK] = {0};
     uint32_t cx = 1;
     for (int q = 0; q < k; ++q) {
         const bnpp_operand &op = ops[q];
@@ -307,8 +390,8 @@ int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *ou
         uint64_t dense = 1, maxoff = 0;
         for (int i = op.scope.rank - 1; i >= 0; --i) {
             const uint32_t var = op.scope.var_id[i], card = op.scope.card[i];
-            const uint64_t st = op.stride ? (uint64_t)op.stride[i] : dense;
             if (op.stride && op.stride[i] < 0) return fail(ctx, BNPP_EINVAL, "negative stride");
+            const uint64_t st = op.stride ? (uint64_t)op.stride[i] : dense;
             dense *= card;
             maxoff += (uint64_t)(card - 1) * st;
             for (int j = i + 1; j < op.scope.rank; ++j)
@@ -327,40 +410,59 @@ int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *ou
             axes[pos].s[q] = st;
         }
         if (maxoff >= (1ull << 32)) return fail(ctx, BNPP_ETOOBIG, "operand table has >= 2^32 entries");
+        op_bytes[q] = 8 * dense;
     }
 
-    // drop size-1 axes, then merge neighbours that are contiguous in the output and in every operand
+    // ---- iteration order -------------------------------------------------------
+    // keep the output's fastest axes (>= kTileOutputs entries) in place; above them iterate
+    // fastest the axes that large operands lack, so their tiles are re-read from L2
+    std::vector<Axis> it;
+    for (int i = 0; i < wr; ++i)
+        if (axes[i].ext > 1) it.push_back(axes[i]);
+    {
+        size_t first_tile = it.size();
+        uint64_t cover = 1;
+        while (first_tile > 0 && cover < kTileOutputs) cover *= it[--first_tile].ext;
+        bool any = false;
+        for (size_t a = 0; a < first_tile; ++a) {
+            for (int q = 0; q < k; ++q)
+                if (it[a].s[q] == 0 && op_bytes[q] > kReuseBytes) it[a].miss += op_bytes[q];
+            any |= it[a].miss != 0;
+        }
+        if (any)
+            std::stable_sort(it.begin(), it.begin() + first_tile, [](const Axis &x, const Axis &y) { return x.miss < y.miss; });
+    }
+
+    // merge neighbours that are contiguous in the output and in every operand
     std::vector<Axis> m;
-    for (int i = 0; i < wr; ++i) {
-        if (axes[i].ext == 1) continue;
+    for (size_t i = 0; i < it.size(); ++i) {
         if (!m.empty()) {
-            Axis &o = m.back();   // o is OUTER to axes[i]
-            bool ok = (o.so == axes[i].so * axes[i].ext);
-            for (int q = 0; q < k && ok; ++q) ok = (o.s[q] == axes[i].s[q] * axes[i].ext);
-            if (ok && (uint64_t)o.ext * axes[i].ext < (1ull << 32)) {
-                o.ext *= axes[i].ext;
-                o.so = axes[i].so;
-                for (int q = 0; q < k; ++q) o.s[q] = axes[i].s[q];
+            Axis &o = m.back();   // o is OUTER to it[i]
+            bool ok = (o.so == it[i].so * it[i].ext);
+            for (int q = 0; q < k && ok; ++q) ok = (o.s[q] == it[i].s[q] * it[i].ext);
+            if (ok && (uint64_t)o.ext * it[i].ext < (1ull << 32)) {
+                o.ext *= it[i].ext;
+                o.so = it[i].so;
+                for (int q = 0; q < k; ++q) o.s[q] = it[i].s[q];
                 continue;
             }
         }
-        m.push_back(axes[i]);
+        m.push_back(it[i]);
     }
-    if ((int)m.size() > kMaxR) return fail(ctx, BNPP_ERANK, "more than BNPP_MAX_AXES non-mergeable axes");
 
-    ContractParams p;
-    memset(&p, 0, sizeof p);
     const bool generic = (cx > 2);
     const int C = generic ? 0 : (int)cx;
     int V = 1;
     if (!generic && !m.empty() && (m.back().ext % 2 == 0)) V = 2;
 
+    ParamsHead h;
+    memset(&h, 0, sizeof h);
     for (int q = 0; q < k; ++q) {
-        p.in[q] = ops[q].data;
-        p.sx[q] = (uint32_t)sx[q];
-        p.sl[q] = m.empty() ? 0 : (uint32_t)m.back().s[q];
+        h.in[q] = ops[q].data;
+        h.sx[q] = (uint32_t)sx[q];
+        h.sl[q] = m.empty() ? 0 : (uint32_t)m.back().s[q];
     }
-    const uint32_t sol = m.empty() ? 0 : (uint32_t)m.back().so;
+    h.sol = m.empty() ? 0 : (uint32_t)m.back().so;
     if (V == 2) {
         Axis &l = m.back();
         l.ext /= 2;
@@ -368,64 +470,93 @@ int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *ou
         for (int q = 0; q < k; ++q) l.s[q] *= 2;
         if (l.ext == 1) m.pop_back();
     }
-    p.R = (uint32_t)m.size();
-    for (uint32_t a = 0; a < p.R; ++a) {
+    const uint32_t R = (uint32_t)m.size();
+    h.n_items = n_out / V;
+    h.cx = cx;
+    h.out = out_dev;
+    h.out_vec = (V == 2 && h.sol == 1 && aligned(out_dev, 16)) ? 1 : 0;
+    for (uint32_t a = 0; a < R && h.out_vec; ++a)
+        if (m[a].so % 2) h.out_vec = 0;
+
+    // load class per operand: how the [V x C] micro-tile sits in the operand's memory
+    for (int q = 0; q < k && !generic; ++q) {
+        const uint32_t x = h.sx[q], l = (V == 2) ? h.sl[q] : 0;
+        bool mult2 = true, mult4 = true;
+        for (uint32_t a = 0; a < R; ++a) {
+            if (m[a].s[q] % 2) mult2 = false;
+            if (m[a].s[q] % 4) mult4 = false;
+        }
+        const bool has_x = (C == 2 && x != 0), has_l = (V == 2 && l != 0);
+        uint8_t c;
+        if (!has_x && !has_l) c = LC_BCAST;
+        else if (has_x && x == 1 && mult2 && aligned(h.in[q], 16) && (!has_l || l % 2 == 0)) {
+            if (!has_l) c = LC_VX_B;
+            else if (l == 2 && mult4 && aligned(h.in[q], 32)) c = LC_V4;
+            else c = LC_VX;
+        } else if (has_l && l == 1 && mult2 && aligned(h.in[q], 16) && (!has_x || x % 2 == 0)) {
+            if (!has_x) c = LC_VL_B;
+            else if (x == 2 && mult4 && aligned(h.in[q], 32)) c = LC_V4T;
+            else c = LC_VL;
+        } else if (has_x && has_l) c = LC_S_JX;
+        else c = has_x ? LC_S_X : LC_S_L;
+        h.cls[q] = c;
+    }
+
+    h.partials = ctx->partials;
+    h.ticket = ctx->ticket;
+    h.z = z_dev ? z_dev : ctx->scratch_z;
+    h.status = ctx->status;
+
+    // ---- power-of-two iteration space: per-operand bit-fields --------------------
+    bool p2 = true;
+    for (uint32_t a = 0; a < R; ++a) p2 = p2 && is_pow2(m[a].ext);
+    if (p2) {
+        ParamsP2 p;
+        memset(&p, 0, sizeof p);
+        p.h = h;
+        bool fits = true;
+        for (int q = 0; q <= k && fits; ++q) {
+            int nf = 0;
+            uint32_t sh = 0;
+            // walk axes innermost first; a field grows while the next axis continues it in THIS operand
+            uint32_t cur_sh = 0, cur_bits = 0;
+            uint64_t cur_mul = 0;
+            for (int a = (int)R - 1; a >= 0; --a) {
+                const uint32_t bits = ilog2(m[a].ext);
+                const uint64_t st = (q == k) ? m[a].so : m[a].s[q];
+                if (cur_bits && st == (cur_mul << cur_bits) && st != 0) {
+                    cur_bits += bits;
+                } else {
+                    if (cur_bits && cur_mul) {
+                        if (nf == kMaxF) { fits = false; break; }
+                        p.f[q][nf++] = Field{(cur_bits >= 32) ? 0xffffffffu : ((1u << cur_bits) - 1), (uint32_t)cur_mul, cur_sh};
+                    }
+                    cur_sh = sh;
+                    cur_bits = bits;
+                    cur_mul = st;
+                }
+                sh += bits;
+            }
+            if (fits && cur_bits && cur_mul) {
+                if (nf == kMaxF) fits = false;
+                else p.f[q][nf++] = Field{(cur_bits >= 32) ? 0xffffffffu : ((1u << cur_bits) - 1), (uint32_t)cur_mul, cur_sh};
+            }
+            p.nf[q] = (uint8_t)nf;
+        }
+        if (fits) return launch(ctx, p, k, C, V, divide != 0, generic, "p2", R);
+    }
+
+    if ((int)R > kMaxR) return fail(ctx, BNPP_ERANK, "more than BNPP_MAX_AXES non-mergeable axes");
+    ParamsMR p;
+    memset(&p, 0, sizeof p);
+    p.h = h;
+    p.R = R;
+    for (uint32_t a = 0; a < R; ++a) {
         p.div[a] = make_fastdiv(m[a].ext);
         p.so[a] = (uint32_t)m[a].so;
         for (int q = 0; q < k; ++q) p.s[q][a] = (uint32_t)m[a].s[q];
     }
-    p.n_items = n_out / V;
-    p.cx = cx;
-    p.out = out_dev;
-    p.out_vec = (V == 2 && sol == 1 && aligned(out_dev, 16)) ? 1 : 0;
-
-    // load class per operand: how the [V x C] micro-tile sits in the operand's memory
-    for (int q = 0; q < k && !generic; ++q) {
-        const uint32_t x = p.sx[q], l = (V == 2) ? p.sl[q] : 0;
-        uint32_t g = 0;   // gcd-like: every item offset is a multiple of 2 / 4 elements?
-        bool mult2 = true, mult4 = true;
-        for (uint32_t a = 0; a < p.R; ++a) {
-            if (p.s[q][a] % 2) mult2 = false;
-            if (p.s[q][a] % 4) mult4 = false;
-        }
-        (void)g;
-        const bool has_x = (C == 2 && x != 0), has_l = (V == 2 && l != 0);
-        uint8_t c = LC_SCALAR;
-        if (!has_x && !has_l) c = LC_BCAST;
-        else if (has_x && x == 1 && mult2 && aligned(p.in[q], 16) && (!has_l || l % 2 == 0)) {
-            if (!has_l) c = LC_VX_B;
-            else if (l == 2 && mult4 && aligned(p.in[q], 32)) c = LC_V4;
-            else c = LC_VX;
-        } else if (has_l && l == 1 && mult2 && aligned(p.in[q], 16) && (!has_x || x % 2 == 0)) {
-            if (!has_x) c = LC_VL_B;
-            else if (x == 2 && mult4 && aligned(p.in[q], 32)) c = LC_V4T;
-            else c = LC_VL;
-        }
-        p.cls[q] = c;
-    }
-
-    p.partials = ctx->partials;
-    p.ticket = ctx->ticket;
-    p.z = z_dev ? z_dev : ctx->scratch_z;
-    p.status = ctx->status;
-
-    uint64_t blocks = (p.n_items + kBlock - 1) / kBlock;
-    const uint64_t cap = (uint64_t)ctx->sm_count * 8;   // persistent grid: 8 CTAs of 256 threads per SM
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-
-    kernel_fn fn = pick(k, C, V, divide != 0, generic);
-    fn<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(p);
-    BNPP_CUDA(ctx, cudaGetLastError());
-    ctx->launches++;
-    char nm[96];
-    if (generic) snprintf(nm, sizeof nm, "contract_generic<K=%d,div=%d> cx=%u R=%u", k, divide != 0, cx, p.R);
-    else snprintf(nm, sizeof nm, "contract_fast<K=%d,C=%d,V=%d,div=%d> R=%u cls=%d,%d,%d", k, C, V, divide != 0, p.R,
-                  p.cls[0], k > 1 ? p.cls[1] : -1, k > 2 ? p.cls[2] : -1);
-    ctx->last_kernel = nm;
-    ctx->last_grid = (uint32_t)blocks;
-    ctx->last_block = kBlock;
-    return BNPP_OK;
+    return launch(ctx, p, k, C, V, divide != 0, generic, "mr", R);
 }
 
 }  // namespace bnpp

@@ -58,5 +58,5 @@ class FactorGraph:
         """FactorGraph::marginal for every variable, code/graph.cpp:393-403 -> list of arrays"""
         out = np.zeros(int(self.cards.sum()))
         self.ctx.check(self.ctx.L.bnpp_fg_marginals(self.h, out.ctypes.data_as(capi.c_f64p)))
-        off = np.concatenate([[0], np.cumsum(self.cards)])
+        off = [0] + [int(x) for x in np.cumsum(self.cards)]
         return [out[off[v]:off[v + 1]] for v in range(len(self.cards))]

@@ -57,10 +57,10 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(1)
     cache = {}
 
-    def table(scope):
-        key = len(scope)
+    def table(scope, which):
+        key = (len(scope), which)     # A and B must never alias: the kernel would read one table only
         if key not in cache:
-            f = DeviceFactor.empty(ctx, list(range(key)), [2] * key)
+            f = DeviceFactor.empty(ctx, list(range(key[0])), [2] * key[0])
             f.buf[:-1] = torch.rand(f.size, generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
             cache[key] = f
         return cache[key]
@@ -71,7 +71,7 @@ def main():
             continue
         if rev and args.no_reverse:
             continue
-        A, B = table(sa), table(sb)
+        A, B = table(sa, 'A'), table(sb, 'B')
         union = sa + [v for v in sb if v not in sa]
         out_scope = [v for v in union if v != k]
         out = DeviceFactor.empty(ctx, out_scope, [2] * len(out_scope))
