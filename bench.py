@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the bn-pp factor-algebra hot path on B200.
+
+Metric (BASELINE.json): factor entries/sec of fused product+sum-out, measured on
+config 4: exact PR by variable elimination (min-fill) on the synthetic "wide" Bayesian
+network whose largest elimination step is a 2^28-entry fp64 union table.
+
+One step = one full PR query: every bucket of the elimination order is one fused
+product+sum-out launch, intermediates stay in HBM.  "entries" = sum over the
+elimination steps of the union-table size.
+
+  value : device-timed, CPTs already resident, plan prebuilt.
+  e2e   : BN.partition(evidence, "mf") from HOST buffers each step: pinned CPTs -> H2D,
+          min-fill ordering on the host, planning, the launches, scalar -> D2H.
+  roofline : the widest fused launch, algorithmic bytes 8*(sum #operands + #out) over its
+          CUDA-event duration inside the timed region, against MEASURED_PEAKS.json.
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref) on a bounded sample of the same
+          generator (narrower network), one core -- it is single-threaded.
+
+N > 1 (torchrun): the network is too wide for one GPU by log2(N) variables; each rank
+eliminates the slab of the wide factors selected by fixing those variables to its rank's
+bits, and the cross-shard sum-out of the shard variables is one NCCL all-reduce of the
+partition.  Per-GPU work stays fixed as N grows => "scaling": "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "factor entries/sec (fused product+sum-out), VE PR on 2^28-entry tables"
+UNIT = "entries/s"
+
+# config 4 per GPU count: (N, W, K, seed) of bnpp_b200.synth.random_bn_uai and the min-fill width
+WIDE = {1: (64, 40, 4, 5), 2: (64, 40, 4, 3), 4: (64, 40, 4, 6), 8: (64, 40, 4, 8)}
+# bounded CPU sample: same generator, narrower (the reference needs ~1 us per entry)
+CPU_SAMPLE = (48, 26, 4, 3)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_leg(steps=1):
+    """times the unmodified reference (oracle/_ref/ref_harness, 1 thread) on the bounded sample"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    from bnpp_b200 import model, synth
+    N, W, K, seed = CPU_SAMPLE
+    text = synth.random_bn_uai(N, W, K, seed)
+    scopes, _ = synth.random_bn_scopes(N, W, K, seed)
+    order, width = model.elim_order([2] * N, scopes, list(range(N)), "mf")
+    entries = union_entries(scopes, order)
+    path = "/tmp/bnpp_cpu_sample_%d.uai" % os.getpid()
+    with open(path, "w") as f:
+        f.write(text)
+    if orc.have_ref():
+        kind = "reference"
+        ms = []
+        for _ in range(steps):
+            rows = orc.RefHarness().run(["model " + path, "opt mf", "pr"], timeout=3000)
+            pr = [r for r in rows if r[0] == "PR"][0]
+            ms.append(float(pr[2]))
+            z = float(pr[1])
+    else:
+        kind = "port"
+        m = orc.read_uai(path)
+        ms = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            z = orc.partition(m, {}, order)
+            ms.append((time.perf_counter() - t0) * 1e3)
+    os.unlink(path)
+    t = sum(ms) / len(ms)
+    return {"value": entries / t * 1e3, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "same generator N=%d W=%d K=%d seed=%d (min-fill width %d, %d union entries per query), "
+                      "%d query(ies), %.1f s each; Z=%.12g" % (N, W, K, seed, width, entries, steps, t / 1e3, z)}, t
+
+
+def union_entries(scopes, order):
+    """sum over elimination steps of the union-table size (binary variables), bucket elimination"""
+    rank = {v: i for i, v in enumerate(order)}
+    buckets = {v: [] for v in order}
+    for sc in scopes:
+        live = [v for v in sc if v in rank]
+        if live:
+            buckets[min(live, key=rank.get)].append(set(live))
+    total = 0
+    for v in order:
+        if not buckets[v]:
+            continue
+        u = set().union(*buckets[v])
+        total += 2 ** len(u)
+        u.discard(v)
+        if u:
+            buckets[min(u, key=rank.get)].append(u)
+    return total
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb, t_ms = cpu_reference_leg(max(1, min(args.steps, 3)))
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "config 4 generator, bounded CPU sample: " + cb["sample"]},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from bnpp_b200 import capi, model, synth
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    ctx = capi.Context(local)
+    stream = ctx.torch_stream
+
+    n_gpus = world
+    if n_gpus not in WIDE:
+        raise SystemExit("bench.py supports 1, 2, 4 or 8 GPUs")
+    N, W, K, seed = WIDE[n_gpus]
+    text = synth.random_bn_uai(N, W, K, seed)
+    _, bn = model.from_uai_text(ctx, text)
+    full_order, full_width = bn.order(list(range(N)), {}, "mf")
+
+    # wide-factor sharding: the log2(N) variables of the widest clique that are eliminated last
+    shard_vars, evidence = [], {}
+    if n_gpus > 1:
+        g = n_gpus.bit_length() - 1
+        shard_vars = pick_shard_vars(bn.scopes, full_order, g)
+        evidence = {v: (rank >> i) & 1 for i, v in enumerate(shard_vars)}
+    variables = [v for v in range(N) if v not in evidence]
+
+    def one_query_device(plan, obs_val, res):
+        plan.run(bn.table_ptrs, obs_val, res.data_ptr(), res.data_ptr() + 8)
+
+    # ---- device-timed value: plan prebuilt, tables resident --------------------------------
+    order, width = bn.order(variables, evidence, "mf")
+    plan = bn.plan(sorted(evidence), order)
+    obs_val = [evidence[v] for v in sorted(evidence)]
+    with torch.cuda.stream(stream):
+        res = torch.zeros(2, dtype=torch.float64, device="cuda")
+    for _ in range(args.warmup):
+        one_query_device(plan, obs_val, res)
+    ctx.sync()
+    plan.set_profiling(True)
+    per_launch = None
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        one_query_device(plan, obs_val, res)
+        st = plan.step_stats()          # synchronises on the last launch of this query
+        per_launch = st if per_launch is None else [
+            dict(a, ms=a["ms"] + b["ms"]) for a, b in zip(per_launch, st)]
+    if world > 1:
+        with torch.cuda.stream(stream):
+            zall = res[1:].clone()
+            dist.all_reduce(zall)       # cross-shard sum-out of the shard variables: one double over NVLink
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dev_ms = e0.elapsed_time(e1)
+    gpu_launches = ctx.launches - launches0
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    z_local = float(res[1].item())
+    z_total = float(zall.item()) if world > 1 else z_local
+    entries_rank = plan.union_entries
+    ent = torch.tensor([float(entries_rank)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ent)
+    entries_all = float(ent.item())
+    value = entries_all * args.steps / (dev_ms / 1e3)
+    plan.set_profiling(False)
+
+    # ---- e2e: through the public API from host buffers -----------------------------------------
+    for _ in range(2):
+        bn._plans.clear()
+        bn.reupload()
+        bn.partition(evidence, "mf")
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bn._plans.clear()               # nothing cached: ordering + planning are paid every step
+        bn.reupload()                   # pinned host CPTs -> HBM
+        z_e2e, _ = bn.partition(evidence, "mf")     # ... launches ... scalar -> host
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = entries_all * args.steps / e2e_s
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel: the widest fused launch ---------------------------------
+    peak, peak_kind = peaks()
+    widest = max(range(len(per_launch)), key=lambda i: per_launch[i]["bytes"])
+    wl = per_launch[widest]
+    w_ms = wl["ms"] / args.steps
+    achieved = wl["bytes"] / w_ms / 1e6
+    big = [s for s in per_launch if s["entries"] >= (1 << 24)]
+    big_bytes = sum(s["bytes"] for s in big)
+    big_ms = sum(s["ms"] for s in big) / args.steps
+    all_ms = sum(s["ms"] for s in per_launch) / args.steps
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_kind": peak_kind,
+                "kernel": "contract_fast (fused product+sum-out), widest launch: k=%d operands, %d union entries, "
+                          "%.3f GB algorithmic, %.3f ms" % (wl["k"], wl["entries"], wl["bytes"] / 1e9, w_ms),
+                "launches_ge_2p24_entries": {"n": len(big), "GBs": big_bytes / big_ms / 1e6 if big_ms else None,
+                                             "frac": big_bytes / big_ms / 1e6 / peak if big_ms else None,
+                                             "share_of_step_ms": big_ms / all_ms if all_ms else None}}
+
+    cb = None
+    if not args.no_cpu_baseline:
+        cb, _ = cpu_reference_leg(1)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config 4: synthetic random BN N=%d W=%d K=%d seed=%d, exact PR via VE (min-fill width %d%s); "
+                                   "%d fused launches per query, %d union entries per rank, largest union table 2^%d entries"
+                                   % (N, W, K, seed, full_width,
+                                      (", sharded on variables %s -> width %d per rank" % (shard_vars, width)) if shard_vars else "",
+                                      plan.n_launches, entries_rank, plan.max_step_entries.bit_length() - 1),
+                       "l2_flush": "inputs larger than L2: every step streams %.1f GB of tables through a 126 MB L2"
+                                   % (plan.bytes / 1e9),
+                       "partition": z_total, "partition_e2e": z_e2e, "peak_intermediate_GB": plan.peak_bytes / 1e9},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bn.h2d_bytes, "d2h_bytes_per_step": 16,
+                    "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches": gpu_launches, "clocks": sampler.summary(), "roofline": roofline, "cpu_baseline": cb}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def pick_shard_vars(scopes, order, g):
+    """the g variables of the widest elimination clique that the order eliminates last"""
+    rank = {v: i for i, v in enumerate(order)}
+    buckets = {v: [] for v in order}
+    for sc in scopes:
+        buckets[min(sc, key=rank.get)].append(set(sc))
+    best, best_u = -1, None
+    for v in order:
+        if not buckets[v]:
+            continue
+        u = set().union(*buckets[v])
+        if len(u) > best:
+            best, best_u = len(u), set(u)
+        u.discard(v)
+        if u:
+            buckets[min(u, key=rank.get)].append(u)
+    return sorted(best_u, key=rank.get)[-g:]
+
+
+if __name__ == "__main__":
+    sys.exit(main())

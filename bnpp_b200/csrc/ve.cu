@@ -1,0 +1,380 @@
+// Device-resident variable elimination: plan + executor.
+//
+// Replaces the bucket-elimination loop of BN::variable_elimination (reference
+// code/model.cpp:382-445) together with the up-front conditioning of every CPT
+// (code/model.cpp:283-286, 321-324):
+//   * evidence is never materialised -- a conditioned CPT is a strided VIEW of the
+//     resident table whose base offset is computed from the evidence values at run
+//     time (code/factor.cpp:214-242 reduced to pointer arithmetic);
+//   * each bucket is ONE fused kernel launch (product of the bucket, sum out the
+//     variable), never writing the product table (code/model.cpp:414-418);
+//   * intermediates stay in HBM from the first bucket to the final scalar; only the
+//     result crosses back to the host.
+// The reference leaves the axis order of intermediates to the iteration order of an
+// address-keyed hash set; here it is CANONICAL: axes sorted by
+// elimination time, the next variable to be eliminated innermost.  Every operand of a
+// bucket then has the eliminated variable as its fastest axis (32-byte loads) and
+// scopes are mutually order-compatible (pure broadcasts, no transposes).
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "common.cuh"
+#include "elim_order.hpp"
+
+namespace bnpp {
+int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope, int64_t elim_var, int divide,
+             double *out_dev, double *z_dev);
+int fill(bnpp_ctx *ctx, double *out, uint64_t n, double value);
+
+struct PlanFactor {
+    std::vector<uint32_t> var, card;
+    std::vector<int64_t> stride;            // empty = dense over (var, card)
+    int src = -1;                           // >= 0: view of input table `src`; -1: intermediate
+    std::vector<std::pair<int64_t, int>> obs;   // (stride, index into obs_val) folded into the base at run time
+    uint64_t size = 1;                      // entries addressed
+    int last_use = -1;                      // step index after which an intermediate is freed
+};
+
+struct PlanStep {
+    std::vector<int> operands;
+    int out = -1;                           // PlanFactor index, or -2 = the caller's result buffer
+    int64_t elim = -1;
+    uint64_t union_entries = 0, bytes = 0;
+};
+}  // namespace bnpp
+
+struct bnpp_ve_plan {
+    bnpp_ctx *ctx = nullptr;
+    int n_inputs = 0;
+    std::vector<bnpp::PlanFactor> f;
+    std::vector<bnpp::PlanStep> steps;
+    std::vector<uint32_t> result_var, result_card;
+    uint64_t result_size = 1;
+    uint64_t union_entries = 0, bytes = 0, peak_bytes = 0, max_step_entries = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<float> step_ms;
+};
+
+using namespace bnpp;
+
+namespace {
+
+uint64_t table_size(const std::vector<uint32_t> &card)
+{
+    uint64_t n = 1;
+    for (uint32_t c : card) n *= c;
+    return n;
+}
+
+// one fused launch description: product of `ops`, optionally eliminating `elim`, output
+// in canonical order (descending rank => the lowest-rank variable is the fastest axis)
+int add_step(bnpp_ve_plan *pl, std::vector<int> ops, int64_t elim, const std::map<uint32_t, uint64_t> &rank, bool to_result)
+{
+    std::vector<std::pair<uint64_t, std::pair<uint32_t, uint32_t>>> u;   // (rank, (var, card))
+    for (int id : ops) {
+        const PlanFactor &pf = pl->f[id];
+        for (size_t i = 0; i < pf.var.size(); ++i) {
+            bool seen = false;
+            for (auto &e : u) seen |= (e.second.first == pf.var[i]);
+            if (!seen) u.push_back({rank.at(pf.var[i]), {pf.var[i], pf.card[i]}});
+        }
+    }
+    std::sort(u.begin(), u.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
+    PlanFactor out;
+    uint64_t entries = 1;
+    for (auto &e : u) {
+        entries *= e.second.second;
+        if (elim >= 0 && e.second.first == (uint64_t)elim) continue;
+        out.var.push_back(e.second.first);
+        out.card.push_back(e.second.second);
+    }
+    out.size = table_size(out.card);
+    PlanStep st;
+    st.operands = ops;
+    st.elim = elim;
+    st.union_entries = entries;
+    st.bytes = 8 * out.size;
+    for (int id : ops) st.bytes += 8 * pl->f[id].size;
+    const int step_index = (int)pl->steps.size();
+    for (int id : ops) pl->f[id].last_use = step_index;
+    if (to_result) {
+        st.out = -2;
+        pl->result_var = out.var;
+        pl->result_card = out.card;
+        pl->result_size = out.size;
+    } else {
+        pl->f.push_back(out);
+        st.out = (int)pl->f.size() - 1;
+    }
+    pl->steps.push_back(st);
+    return st.out;
+}
+
+// the kernel takes at most BNPP_MAX_OPERANDS tables: fold the smallest ones first
+void shrink(bnpp_ve_plan *pl, std::vector<int> &ops, const std::map<uint32_t, uint64_t> &rank)
+{
+    while ((int)ops.size() > kMaxK) {
+        std::stable_sort(ops.begin(), ops.end(), [pl](int a, int b) { return pl->f[a].size < pl->f[b].size; });
+        int m = (int)ops.size() - kMaxK + 1;
+        if (m > kMaxK) m = kMaxK;
+        std::vector<int> head(ops.begin(), ops.begin() + m);
+        const int t = add_step(pl, head, -1, rank, false);
+        ops.erase(ops.begin(), ops.begin() + m);
+        ops.insert(ops.begin(), t);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n_obs, const uint32_t *obs_var,
+                        int n_order, const uint32_t *order, bnpp_ve_plan **out)
+{
+    if (!ctx || !out || nfac < 0 || n_obs < 0 || n_order < 0) return BNPP_EINVAL;
+    *out = nullptr;
+    bnpp_ve_plan *pl = new bnpp_ve_plan();
+    pl->ctx = ctx;
+    pl->n_inputs = nfac;
+
+    std::map<uint32_t, int> obs_index;
+    for (int i = 0; i < n_obs; ++i) obs_index[obs_var[i]] = i;
+    std::map<uint32_t, uint64_t> rank;           // elimination time; kept variables after all eliminated ones
+    for (int i = 0; i < n_order; ++i) {
+        if (rank.count(order[i]) || obs_index.count(order[i])) {
+            delete pl;
+            return fail(ctx, BNPP_EINVAL, "elimination order repeats a variable or names an observed one");
+        }
+        rank[order[i]] = (uint64_t)i;
+    }
+
+    // inputs as evidence-reduced views (code/domain.cpp:74-90: free axes keep their order)
+    for (int q = 0; q < nfac; ++q) {
+        const bnpp_scope &s = scopes[q];
+        if (s.rank < 0 || s.rank > BNPP_MAX_RANK) {
+            delete pl;
+            return fail(ctx, BNPP_EINVAL, "bad factor scope");
+        }
+        PlanFactor pf;
+        pf.src = q;
+        uint64_t dense = 1;
+        std::vector<int64_t> st(s.rank);
+        for (int i = s.rank - 1; i >= 0; --i) {
+            st[i] = (int64_t)dense;
+            dense *= s.card[i];
+        }
+        for (int i = 0; i < s.rank; ++i) {
+            auto o = obs_index.find(s.var_id[i]);
+            if (o != obs_index.end()) {
+                pf.obs.push_back({st[i], o->second});
+                continue;
+            }
+            pf.var.push_back(s.var_id[i]);
+            pf.card.push_back(s.card[i]);
+            pf.stride.push_back(st[i]);
+            if (!rank.count(s.var_id[i])) rank[s.var_id[i]] = (1ull << 40) + (0xffffffffull - s.var_id[i]);   // kept: ascending id, most significant first
+        }
+        pf.size = table_size(pf.card);
+        pl->f.push_back(pf);
+    }
+
+    // bucket = factors whose earliest-eliminated variable is order[i] (code/model.cpp:390-406)
+    std::vector<std::vector<int>> bucket(n_order);
+    std::vector<int> leftover;
+    auto place = [&](int id) {
+        uint64_t best = UINT64_MAX;
+        for (uint32_t v : pl->f[id].var) best = std::min(best, rank.at(v));
+        if (best < (uint64_t)n_order) bucket[best].push_back(id);
+        else leftover.push_back(id);
+    };
+    for (int q = 0; q < nfac; ++q) place(q);
+
+    // eliminate in order (code/model.cpp:409-439)
+    for (int i = 0; i < n_order; ++i) {
+        std::vector<int> ops = bucket[i];
+        if (ops.empty()) continue;    // the reference makes a scalar 1 here; multiplying by it changes nothing
+        shrink(pl, ops, rank);
+        const int t = add_step(pl, ops, (int64_t)order[i], rank, false);
+        pl->union_entries += pl->steps.back().union_entries;
+        pl->max_step_entries = std::max(pl->max_step_entries, pl->steps.back().union_entries);
+        place(t);
+    }
+    // result = product of everything that never entered (or left) a bucket (code/model.cpp:403-405, 436-438)
+    if (leftover.empty()) {
+        pl->result_size = 1;
+    } else {
+        shrink(pl, leftover, rank);
+        add_step(pl, leftover, -1, rank, true);
+    }
+
+    // statistics: bytes, and the peak of live intermediates
+    uint64_t live = 0;
+    for (size_t s = 0; s < pl->steps.size(); ++s) {
+        const PlanStep &st = pl->steps[s];
+        pl->bytes += st.bytes;
+        if (st.out >= 0) live += 8 * pl->f[st.out].size;
+        pl->peak_bytes = std::max(pl->peak_bytes, live);
+        for (int id : st.operands)
+            if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) live -= 8 * pl->f[id].size;
+    }
+    *out = pl;
+    return BNPP_OK;
+}
+
+int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
+{
+    if (!pl) return BNPP_OK;
+    for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
+    delete pl;
+    return BNPP_OK;
+}
+
+int bnpp_ve_plan_info(const bnpp_ve_plan *pl, int32_t *result_rank, uint32_t *result_var, uint32_t *result_card,
+                      uint64_t *n_launches, uint64_t *union_entries, uint64_t *algorithmic_bytes,
+                      uint64_t *peak_bytes, uint64_t *max_step_entries)
+{
+    if (!pl) return BNPP_EINVAL;
+    if (result_rank) *result_rank = (int32_t)pl->result_var.size();
+    for (size_t i = 0; i < pl->result_var.size(); ++i) {
+        if (result_var) result_var[i] = pl->result_var[i];
+        if (result_card) result_card[i] = pl->result_card[i];
+    }
+    if (n_launches) *n_launches = pl->steps.size();
+    if (union_entries) *union_entries = pl->union_entries;
+    if (algorithmic_bytes) *algorithmic_bytes = pl->bytes;
+    if (peak_bytes) *peak_bytes = pl->peak_bytes;
+    if (max_step_entries) *max_step_entries = pl->max_step_entries;
+    return BNPP_OK;
+}
+
+int bnpp_ve_plan_set_profiling(bnpp_ve_plan *pl, int on)
+{
+    if (!pl) return BNPP_EINVAL;
+    pl->profiling = on != 0;
+    if (pl->profiling && pl->ev.size() < pl->steps.size() + 1) {
+        const size_t need = pl->steps.size() + 1;
+        while (pl->ev.size() < need) {
+            cudaEvent_t e;
+            BNPP_CUDA(pl->ctx, cudaEventCreate(&e));
+            pl->ev.push_back(e);
+        }
+    }
+    return BNPP_OK;
+}
+
+int bnpp_ve_plan_step_stats(bnpp_ve_plan *pl, uint64_t n, float *ms, uint64_t *bytes, uint64_t *entries, int32_t *k)
+{
+    if (!pl) return BNPP_EINVAL;
+    if (pl->profiling && !pl->ev.empty()) {
+        BNPP_CUDA(pl->ctx, cudaEventSynchronize(pl->ev[pl->steps.size()]));
+        pl->step_ms.resize(pl->steps.size());
+        for (size_t s = 0; s < pl->steps.size(); ++s)
+            BNPP_CUDA(pl->ctx, cudaEventElapsedTime(&pl->step_ms[s], pl->ev[s], pl->ev[s + 1]));
+    }
+    for (size_t s = 0; s < pl->steps.size() && s < n; ++s) {
+        if (ms) ms[s] = s < pl->step_ms.size() ? pl->step_ms[s] : 0.0f;
+        if (bytes) bytes[s] = pl->steps[s].bytes;
+        if (entries) entries[s] = pl->steps[s].union_entries;
+        if (k) k[s] = (int32_t)pl->steps[s].operands.size();
+    }
+    return BNPP_OK;
+}
+
+int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const uint32_t *obs_val, double *result_dev,
+                     double *z_dev)
+{
+    if (!pl || !result_dev) return BNPP_EINVAL;
+    bnpp_ctx *ctx = pl->ctx;
+    std::vector<const double *> ptr(pl->f.size(), nullptr);
+    for (size_t i = 0; i < pl->f.size(); ++i) {
+        const PlanFactor &pf = pl->f[i];
+        if (pf.src < 0) continue;
+        uint64_t base = 0;
+        for (auto &o : pf.obs) base += (uint64_t)o.first * obs_val[o.second];
+        ptr[i] = tables_dev[pf.src] + base;
+    }
+    if (pl->steps.empty() || pl->steps.back().out != -2) {
+        int rc = fill(ctx, result_dev, 1, 1.0);   // no factor left: the scalar 1 (code/model.cpp:355)
+        if (rc != BNPP_OK) return rc;
+        if (z_dev) rc = fill(ctx, z_dev, 1, 1.0);
+        if (rc != BNPP_OK) return rc;
+    }
+    std::vector<double *> owned(pl->f.size(), nullptr);
+    int rc = BNPP_OK;
+    for (size_t s = 0; s < pl->steps.size() && rc == BNPP_OK; ++s) {
+        const PlanStep &st = pl->steps[s];
+        if (pl->profiling) cudaEventRecord(pl->ev[s], ctx->stream);
+        bnpp_operand ops[kMaxK];
+        for (size_t q = 0; q < st.operands.size(); ++q) {
+            const PlanFactor &pf = pl->f[st.operands[q]];
+            ops[q].data = ptr[st.operands[q]];
+            ops[q].scope.rank = (int32_t)pf.var.size();
+            ops[q].scope.var_id = pf.var.data();
+            ops[q].scope.card = pf.card.data();
+            ops[q].stride = pf.stride.empty() ? nullptr : pf.stride.data();
+        }
+        bnpp_scope os;
+        double *dst;
+        if (st.out == -2) {
+            os.rank = (int32_t)pl->result_var.size();
+            os.var_id = pl->result_var.data();
+            os.card = pl->result_card.data();
+            dst = result_dev;
+        } else {
+            const PlanFactor &of = pl->f[st.out];
+            os.rank = (int32_t)of.var.size();
+            os.var_id = of.var.data();
+            os.card = of.card.data();
+            rc = bnpp_alloc(ctx, of.size, &owned[st.out]);
+            if (rc != BNPP_OK) break;
+            dst = owned[st.out];
+            ptr[st.out] = dst;
+        }
+        rc = contract(ctx, (int)st.operands.size(), ops, &os, st.elim, 0, dst, st.out == -2 ? z_dev : nullptr);
+        for (int id : st.operands)
+            if (owned[id] && pl->f[id].last_use == (int)s) {
+                bnpp_free(ctx, owned[id]);
+                owned[id] = nullptr;
+            }
+    }
+    if (pl->profiling) cudaEventRecord(pl->ev[pl->steps.size()], ctx->stream);
+    for (double *p : owned)
+        if (p) bnpp_free(ctx, p);
+    return rc;
+}
+
+// Graph::ordering on the host (code/graph.cpp:41-195), same tie-breaks as the reference.
+// scopes: factor scopes AFTER conditioning; vars: the variables to order, in the caller's order.
+int bnpp_elim_order(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_vars_to_order,
+                    const uint32_t *vars, int heuristic, uint32_t *order_out, uint32_t *width_out)
+{
+    if (nvars < 0 || nfac < 0 || n_vars_to_order < 0 || heuristic < 0 || heuristic > 2) return BNPP_EINVAL;
+    std::vector<std::vector<unsigned>> sc(nfac);
+    for (int f = 0; f < nfac; ++f) sc[f].assign(scopes[f].var_id, scopes[f].var_id + scopes[f].rank);
+    std::vector<unsigned> c(card, card + nvars);
+    InteractionGraph g(sc, c);
+    std::vector<unsigned> v(vars, vars + n_vars_to_order);
+    unsigned width = 0;
+    std::vector<unsigned> order = g.ordering(v, (Heuristic)heuristic, width);
+    for (size_t i = 0; i < order.size(); ++i) order_out[i] = order[i];
+    if (width_out) *width_out = width;
+    return BNPP_OK;
+}
+
+int bnpp_order_width(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_order,
+                     const uint32_t *order, uint32_t *width_out)
+{
+    if (nvars < 0 || nfac < 0 || n_order < 0 || !width_out) return BNPP_EINVAL;
+    std::vector<std::vector<unsigned>> sc(nfac);
+    for (int f = 0; f < nfac; ++f) sc[f].assign(scopes[f].var_id, scopes[f].var_id + scopes[f].rank);
+    std::vector<unsigned> c(card, card + nvars);
+    InteractionGraph g(sc, c);
+    std::vector<unsigned> o(order, order + n_order);
+    *width_out = g.order_width(o);
+    return BNPP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,266 @@
+"""Python mirror of `bn::BN` inference entry points (reference code/model.hh:49-120) over the C ABI.
+
+The CPTs are uploaded to HBM once (`BN(...)`) and stay resident; `partition` /
+`marginals` are BN::partition / BN::marginals (code/model.cpp:250-346): ordering on the
+host with the reference's heuristics and tie-breaks (bnpp_elim_order), then one
+device-resident variable-elimination plan (bnpp_ve_plan_*).  Only the result returns.
+"""
+import ctypes
+import time
+
+import numpy as np
+import torch
+
+from . import capi
+
+HEUR = {"min-fill": 0, "mf": 0, "weighted-min-fill": 1, "wmf": 1, "min-degree": 2, "md": 2}
+
+
+def _declare(L):
+    if getattr(L, "_ve_declared", False):
+        return
+    P = ctypes.POINTER
+    L.bnpp_elim_order.argtypes = [ctypes.c_int, capi.c_u32p, ctypes.c_int, P(capi.Scope), ctypes.c_int, capi.c_u32p,
+                                  ctypes.c_int, capi.c_u32p, capi.c_u32p]
+    L.bnpp_order_width.argtypes = [ctypes.c_int, capi.c_u32p, ctypes.c_int, P(capi.Scope), ctypes.c_int, capi.c_u32p,
+                                   capi.c_u32p]
+    L.bnpp_ve_plan_create.argtypes = [ctypes.c_void_p, ctypes.c_int, P(capi.Scope), ctypes.c_int, capi.c_u32p,
+                                      ctypes.c_int, capi.c_u32p, P(ctypes.c_void_p)]
+    L.bnpp_ve_plan_destroy.argtypes = [ctypes.c_void_p]
+    L.bnpp_ve_plan_info.argtypes = [ctypes.c_void_p, P(ctypes.c_int32), capi.c_u32p, capi.c_u32p, capi.c_u64p,
+                                    capi.c_u64p, capi.c_u64p, capi.c_u64p, capi.c_u64p]
+    L.bnpp_ve_plan_run.argtypes = [ctypes.c_void_p, P(ctypes.c_void_p), capi.c_u32p, ctypes.c_void_p, ctypes.c_void_p]
+    L.bnpp_ve_plan_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.bnpp_ve_plan_step_stats.argtypes = [ctypes.c_void_p, ctypes.c_uint64, P(ctypes.c_float), capi.c_u64p, capi.c_u64p,
+                                          P(ctypes.c_int32)]
+    L._ve_declared = True
+
+
+def _scopes(scope_list, cards):
+    n = len(scope_list)
+    arr = (capi.Scope * max(1, n))()
+    keep = []
+    for i, sc in enumerate(scope_list):
+        s, ka = capi.make_scope(sc, [cards[v] for v in sc])
+        arr[i] = s
+        keep.append(ka)
+    return arr, keep
+
+
+def elim_order(cards, scopes, variables, heuristic):
+    """Graph(...).ordering(variables) of code/graph.cpp:41-101 -> (order, width).  Host only."""
+    L = capi.lib()
+    _declare(L)
+    arr, keep = _scopes(scopes, cards)
+    c = capi._u32(cards)
+    v = capi._u32(variables)
+    out = (ctypes.c_uint32 * max(1, len(variables)))()
+    width = ctypes.c_uint32()
+    rc = L.bnpp_elim_order(len(cards), ctypes.cast(c, capi.c_u32p), len(scopes), arr, len(variables),
+                           ctypes.cast(v, capi.c_u32p), HEUR[heuristic], ctypes.cast(out, capi.c_u32p),
+                           ctypes.byref(width))
+    if rc != 0:
+        raise capi.BnppError(rc, "bnpp_elim_order")
+    return list(out[:len(variables)]), width.value
+
+
+def order_width(cards, scopes, order):
+    """Graph::order_width, code/graph.cpp:197-237"""
+    L = capi.lib()
+    _declare(L)
+    arr, keep = _scopes(scopes, cards)
+    c, o = capi._u32(cards), capi._u32(order)
+    width = ctypes.c_uint32()
+    rc = L.bnpp_order_width(len(cards), ctypes.cast(c, capi.c_u32p), len(scopes), arr, len(order),
+                            ctypes.cast(o, capi.c_u32p), ctypes.byref(width))
+    if rc != 0:
+        raise capi.BnppError(rc, "bnpp_order_width")
+    return width.value
+
+
+class VEPlan:
+    """bnpp_ve_plan: the schedule of fused elimination launches for (scopes, observed ids, order)."""
+
+    def __init__(self, ctx, cards, scopes, observed, order):
+        self.ctx = ctx
+        L = ctx.L
+        _declare(L)
+        arr, self._keep = _scopes(scopes, cards)
+        self.observed = list(observed)
+        ov, od = capi._u32(self.observed), capi._u32(order)
+        h = ctypes.c_void_p()
+        ctx.check(L.bnpp_ve_plan_create(ctx.h, len(scopes), arr, len(self.observed), ctypes.cast(ov, capi.c_u32p),
+                                        len(order), ctypes.cast(od, capi.c_u32p), ctypes.byref(h)))
+        self.h = h
+        rank = ctypes.c_int32()
+        rv = (ctypes.c_uint32 * capi_max_rank())()
+        rc_ = (ctypes.c_uint32 * capi_max_rank())()
+        vals = [ctypes.c_uint64() for _ in range(5)]
+        ctx.check(L.bnpp_ve_plan_info(h, ctypes.byref(rank), ctypes.cast(rv, capi.c_u32p), ctypes.cast(rc_, capi.c_u32p),
+                                      *[ctypes.byref(v) for v in vals]))
+        self.result_scope = list(rv[:rank.value])
+        self.result_cards = list(rc_[:rank.value])
+        self.result_size = int(np.prod(self.result_cards, dtype=np.uint64)) if rank.value else 1
+        self.n_launches, self.union_entries, self.bytes, self.peak_bytes, self.max_step_entries = [v.value for v in vals]
+
+    def run(self, table_ptrs, obs_val, result_ptr, z_ptr=None):
+        n = len(table_ptrs)
+        tp = (ctypes.c_void_p * max(1, n))(*table_ptrs)
+        ov = capi._u32(obs_val)
+        self.ctx.check(self.ctx.L.bnpp_ve_plan_run(self.h, tp, ctypes.cast(ov, capi.c_u32p), ctypes.c_void_p(result_ptr),
+                                                   ctypes.c_void_p(z_ptr) if z_ptr else None))
+
+    def set_profiling(self, on=True):
+        self.ctx.check(self.ctx.L.bnpp_ve_plan_set_profiling(self.h, int(on)))
+
+    def step_stats(self):
+        n = self.n_launches
+        ms = (ctypes.c_float * max(1, n))()
+        by = (ctypes.c_uint64 * max(1, n))()
+        en = (ctypes.c_uint64 * max(1, n))()
+        k = (ctypes.c_int32 * max(1, n))()
+        self.ctx.check(self.ctx.L.bnpp_ve_plan_step_stats(self.h, n, ms, ctypes.cast(by, capi.c_u64p),
+                                                          ctypes.cast(en, capi.c_u64p), k))
+        return [{"ms": ms[i], "bytes": by[i], "entries": en[i], "k": k[i]} for i in range(n)]
+
+    def close(self):
+        if self.h:
+            self.ctx.L.bnpp_ve_plan_destroy(self.h)
+            self.h = None
+
+
+def capi_max_rank():
+    return 64
+
+
+class BN:
+    """Model(name, variables, factors) with the factors resident in HBM (code/model.cpp:14-19)."""
+
+    def __init__(self, ctx, cards, factors):
+        """factors: list of (scope ids, host values) in the reference's layout (last variable fastest)"""
+        self.ctx = ctx
+        self.cards = [int(c) for c in cards]
+        self.scopes = [[int(v) for v in sc] for sc, _ in factors]
+        sizes = [int(np.asarray(v).size) for _, v in factors]
+        # one pinned staging buffer, one H2D copy, tables 32-byte aligned inside one allocation
+        offs, total = [], 0
+        for n in sizes:
+            offs.append(total)
+            total += (n + 3) // 4 * 4
+        self._host = torch.empty(max(1, total), dtype=torch.float64).pin_memory() if torch.cuda.is_available() \
+            else torch.empty(max(1, total), dtype=torch.float64)
+        hv = self._host.numpy()
+        for (sc, v), o, n in zip(factors, offs, sizes):
+            hv[o:o + n] = np.asarray(v, dtype=np.float64).reshape(-1)
+        self.h2d_bytes = 8 * total
+        with torch.cuda.stream(ctx.torch_stream):
+            self._dev = torch.empty(max(1, total), dtype=torch.float64, device="cuda:%d" % ctx.device)
+            self._dev.copy_(self._host, non_blocking=True)
+        self.table_ptrs = [self._dev.data_ptr() + 8 * o for o in offs]
+        self._plans = {}
+
+    @property
+    def nvars(self):
+        return len(self.cards)
+
+    def reupload(self):
+        """host -> device copy of every table (what an end-to-end query pays once per model)"""
+        with torch.cuda.stream(self.ctx.torch_stream):
+            self._dev.copy_(self._host, non_blocking=True)
+
+    def conditioned_scopes(self, observed):
+        return [[v for v in sc if v not in observed] for sc in self.scopes]
+
+    def order(self, variables, observed, heuristic=None):
+        """the order BN::variable_elimination uses (code/model.cpp:358-369)"""
+        if heuristic is None:
+            return list(variables), None
+        return elim_order(self.cards, self.conditioned_scopes(set(observed)), variables, heuristic)
+
+    def plan(self, observed, order):
+        key = (tuple(observed), tuple(order))
+        p = self._plans.get(key)
+        if p is None:
+            p = VEPlan(self.ctx, self.cards, self.scopes, observed, order)
+            self._plans[key] = p
+        return p
+
+    def variable_elimination(self, evidence, order):
+        """-> (result scope, result cards, device tensor of size+1 doubles, partition last)"""
+        observed = sorted(evidence)
+        p = self.plan(observed, order)
+        with torch.cuda.stream(self.ctx.torch_stream):
+            res = torch.empty(p.result_size + 1, dtype=torch.float64, device=self._dev.device)
+        p.run(self.table_ptrs, [evidence[v] for v in observed], res.data_ptr(), res.data_ptr() + 8 * p.result_size)
+        return p.result_scope, p.result_cards, res
+
+    def partition(self, evidence=None, heuristic=None):
+        """BN::partition, VE branch (code/model.cpp:275-294) -> (Z, uptime_ms)"""
+        t0 = time.perf_counter()
+        evidence = dict(evidence or {})
+        variables = [v for v in range(self.nvars) if v not in evidence]
+        order, _ = self.order(variables, evidence, heuristic)
+        scope, cards, res = self.variable_elimination(evidence, order)
+        self.ctx.sync()
+        host = res.cpu()
+        assert host.numel() == 2 and host[0].item() == host[1].item()   # code/model.cpp:288
+        return float(host[1].item()), (time.perf_counter() - t0) * 1e3
+
+    def marginals(self, evidence=None, heuristic=None):
+        """BN::marginals, VE branch (code/model.cpp:320-339): one VE pass per variable, normalised.
+        Observed variables are dropped from the ordering input (the reference crashes there, SURVEY A.2 i)."""
+        evidence = dict(evidence or {})
+        out = []
+        for v in range(self.nvars):
+            variables = [u for u in range(self.nvars) if u != v and u not in evidence]
+            order, _ = self.order(variables, evidence, heuristic)
+            scope, cards, res = self.variable_elimination(evidence, order)
+            n = res.numel() - 1
+            with torch.cuda.stream(self.ctx.torch_stream):
+                nrm = torch.empty(n, dtype=torch.float64, device=res.device)
+            self.ctx.normalize(n, res.data_ptr(), nrm.data_ptr(), z_ptr=res.data_ptr() + 8 * n)
+            out.append(nrm)
+        self.ctx.sync()
+        return [t.cpu().numpy() for t in out]
+
+    def sum_product(self, max_sweeps=10000, epsilon=0.001):
+        """BN::sum_product (code/model.cpp:736-753): evidence is ignored, as in the reference"""
+        from .sumproduct import FactorGraph
+        hv = self._host.numpy()
+        facs = []
+        for sc, p in zip(self.scopes, self.table_ptrs):
+            o = (p - self._dev.data_ptr()) // 8
+            n = int(np.prod([self.cards[v] for v in sc], dtype=np.uint64)) if sc else 1
+            facs.append((sc, hv[o:o + n]))
+        fg = FactorGraph(self.ctx, self.cards, facs)
+        sweeps = fg.update(max_sweeps, epsilon)
+        return fg, sweeps
+
+    def close(self):
+        for p in self._plans.values():
+            p.close()
+        self._plans = {}
+
+
+def from_uai_text(ctx, text):
+    """read_uai_model for tests/bench (the parser itself is the reference's host glue, code/io.cpp:43-100)"""
+    toks = []
+    for line in text.splitlines():
+        for t in line.split():
+            if t.startswith("#"):
+                break
+            toks.append(t)
+    it = iter(toks)
+    kind = next(it)
+    n = int(next(it))
+    cards = [int(next(it)) for _ in range(n)]
+    m = int(next(it))
+    scopes = []
+    for _ in range(m):
+        w = int(next(it))
+        scopes.append([int(next(it)) for _ in range(w)])
+    factors = []
+    for sc in scopes:
+        sz = int(next(it))
+        factors.append((sc, np.array([float(next(it)) for _ in range(sz)])))
+    return kind, BN(ctx, cards, factors)

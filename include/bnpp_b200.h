@@ -128,6 +128,47 @@ int bnpp_normalize(bnpp_ctx *ctx, uint64_t n, const double *in_dev, const double
  * op: 0 = sum, 1 = max, 2 = min.  init is the min's start value. result_dev: device double. */
 int bnpp_reduce(bnpp_ctx *ctx, int op, uint64_t n, const double *in_dev, double init, double *result_dev);
 
+/* ---- device-resident variable elimination -------------------------------------- */
+/* Graph::ordering / min_fill / weighted_min_fill / min_degree (code/graph.cpp:41-195) on
+ * the HOST with the reference's tie-breaks (libstdc++ unordered_set iteration order).
+ * scopes: the factor scopes the graph is built from (already conditioned);
+ * vars: the variables to order, in the caller's order; heuristic: 0 = min-fill,
+ * 1 = weighted min-fill, 2 = min-degree.  Needs no device. */
+int bnpp_elim_order(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_vars_to_order,
+                    const uint32_t *vars, int heuristic, uint32_t *order_out, uint32_t *width_out);
+/* Graph::order_width, code/graph.cpp:197-237 (host). */
+int bnpp_order_width(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_order,
+                     const uint32_t *order, uint32_t *width_out);
+
+/* BN::variable_elimination (code/model.cpp:348-446) over resident tables, preceded by
+ * the conditioning of every factor (code/model.cpp:283-286) expressed as views.
+ *   scopes[nfac]  : ORIGINAL scopes of the dense input tables;
+ *   obs_var[n_obs]: observed variables -- their VALUES are given per run;
+ *   order[n_order]: elimination order over unobserved variables.  Unobserved variables
+ *                   not in `order` are kept: the result is a table over them, ascending
+ *                   variable id, last fastest (the reference leaves this order to a
+ *                   pointer-keyed hash set).
+ * One plan serves any number of runs (other evidence values, other table contents). */
+typedef struct bnpp_ve_plan bnpp_ve_plan;
+int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n_obs, const uint32_t *obs_var,
+                        int n_order, const uint32_t *order, bnpp_ve_plan **out);
+int bnpp_ve_plan_destroy(bnpp_ve_plan *plan);
+/* result scope (arrays of BNPP_MAX_RANK), kernel launches per run, sum over elimination
+ * steps of the union-table entries (the "factor entries" of BASELINE.json's metric), the
+ * algorithmic bytes 8*(sum #operands + #out) over all launches, peak bytes of live
+ * intermediates, and the largest step.  Any pointer may be NULL. */
+int bnpp_ve_plan_info(const bnpp_ve_plan *plan, int32_t *result_rank, uint32_t *result_var, uint32_t *result_card,
+                      uint64_t *n_launches, uint64_t *union_entries, uint64_t *algorithmic_bytes,
+                      uint64_t *peak_bytes, uint64_t *max_step_entries);
+/* tables_dev[nfac]: device tables; obs_val[n_obs]: evidence values; result_dev: device
+ * buffer of the result's size; z_dev: optional device double for its partition.  Asynchronous. */
+int bnpp_ve_plan_run(bnpp_ve_plan *plan, const double *const *tables_dev, const uint32_t *obs_val,
+                     double *result_dev, double *z_dev);
+/* per-launch CUDA-event timing for roofline reports: enable, run, then read
+ * ms / algorithmic bytes / union entries / operand count per launch (synchronises). */
+int bnpp_ve_plan_set_profiling(bnpp_ve_plan *plan, int on);
+int bnpp_ve_plan_step_stats(bnpp_ve_plan *plan, uint64_t n, float *ms, uint64_t *bytes, uint64_t *entries, int32_t *k);
+
 /* ---- factor-graph sum-product (K7), code/graph.cpp:256-403 --------------------- */
 typedef struct bnpp_fg bnpp_fg;
 /* Builds the device edge tables once.  Factor f has scope

@@ -1,0 +1,127 @@
+"""End-to-end parity through the C ABI: BN::partition / BN::marginals by device-resident
+variable elimination (code/model.cpp:250-446) against the unmodified reference's results on
+the same UAI models, evidence and ordering flags.  Tolerance 1e-9 relative (north_star);
+elimination orders are asserted bit-exact on the way."""
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import oracle as orc  # noqa: E402
+from bnpp_b200 import synth  # noqa: E402
+
+REL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from bnpp_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def load(ctx, text):
+    from bnpp_b200 import model
+    return model.from_uai_text(ctx, text)[1]
+
+
+def test_partition_all_models(ctx, golden_models):
+    """configs 1-2 and every small shipped network: PR under no heuristic / -mf / -wmf / -md"""
+    n = 0
+    for name, m in golden_models.items():
+        bn = load(ctx, m["uai"])
+        for case in m["pr"]:
+            ev = {int(k): v for k, v in case["evidence"].items()}
+            variables = [v for v in range(bn.nvars) if v not in ev]
+            if case["flag"]:
+                order, width = bn.order(variables, ev, case["flag"])
+                assert order == case["order"] and width == case["width"], (name, case["flag"])
+            z, _ = bn.partition(ev, case["flag"] or None)
+            assert math.isclose(z, case["pr"], rel_tol=REL), (name, case["flag"], z, case["pr"])
+            n += 1
+        bn.close()
+    assert n > 60
+
+
+def test_marginals(ctx, golden_models):
+    for name in ["asia", "asia_positive", "cancer", "earthquake", "child", "alarm", "grid3x3", "network"]:
+        m = golden_models[name]
+        bn = load(ctx, m["uai"])
+        for case in m["mar"]:
+            ev = {int(k): v for k, v in case["evidence"].items()}
+            got = bn.marginals(ev, case["flag"] or None)
+            for v, (g, want) in enumerate(zip(got, case["mar"])):
+                assert np.allclose(g, want, rtol=REL, atol=0.0), (name, case["flag"], v)
+        bn.close()
+
+
+def test_marginals_heuristic_with_evidence(ctx, golden_models):
+    """`-mar -mf` with evidence crashes in the reference (SURVEY A.2 i); the result must equal the
+    no-heuristic marginals, which the reference does compute"""
+    m = golden_models["alarm"]
+    bn = load(ctx, m["uai"])
+    case = [c for c in m["mar"] if c["evidence"] and not c["flag"]][0]
+    ev = {int(k): v for k, v in case["evidence"].items()}
+    got = bn.marginals(ev, "mf")
+    for g, want in zip(got, case["mar"]):
+        assert np.allclose(g, want, rtol=REL, atol=0.0)
+    bn.close()
+
+
+def test_shipped_goldens(ctx, golden_models):
+    """grid3x3.uai.PR / network.uai.PR as shipped by the reference (log10 Z, 6 digits)"""
+    for name in ("grid3x3", "network"):
+        m = golden_models[name]
+        bn = load(ctx, m["uai"])
+        ev = orc.parse_evidence(m["shipped"]["PR_evid"]) if name == "grid3x3" else {}
+        z, _ = bn.partition(ev, "mf")
+        assert abs(math.log10(z) - float(m["shipped"]["PR"].split()[-1])) < 5e-4
+        bn.close()
+
+
+def test_synthetic_bn(ctx, golden_synth):
+    """config 4 at reduced width: PR vs the reference, and Z = 1 without evidence"""
+    for rec in golden_synth["bn"]:
+        bn = load(ctx, synth.random_bn_uai(rec["N"], rec["W"], rec["K"], rec["seed"]))
+        ev = {int(k): v for k, v in rec["evidence"].items()}
+        for case in rec["cases"]:
+            z, _ = bn.partition(ev, case["flag"])
+            if "pr" in case:
+                assert math.isclose(z, case["pr"], rel_tol=REL), (rec["N"], case["flag"])
+            if not ev:
+                assert math.isclose(z, 1.0, rel_tol=REL)
+        bn.close()
+
+
+def test_evidence_batch_sample(ctx, golden_synth):
+    """config 5: evidence sets over one plan (fixed observed ids) and over varying ids"""
+    for rec in golden_synth["batch"]:
+        bn = load(ctx, synth.random_bn_uai(rec["N"], rec["W"], rec["K"], rec["seed"]))
+        evs = synth.evidence_batch(rec["N"], rec["nobs"], rec["nsets"], seed=5, fixed_ids=rec["fixed_ids"])
+        for i, ev in enumerate(evs):
+            z, _ = bn.partition(ev, "mf")
+            assert math.isclose(z, rec["pr"][i], rel_tol=REL), (rec["N"], i)
+        if rec["fixed_ids"]:
+            assert len(bn._plans) == 1          # one ordering, one plan, evidence values only move base pointers
+        bn.close()
+
+
+def test_wide_bn_normalised(ctx):
+    """a BN without evidence sums to 1: width-22 instance of the config-4 generator (2^23-entry tables)"""
+    from bnpp_b200 import model
+    text = synth.random_bn_uai(56, 30, 4, 2)
+    bn = load(ctx, text)
+    order, width = bn.order(list(range(bn.nvars)), {}, "mf")
+    assert 18 <= width <= 26
+    z, _ = bn.partition({}, "mf")
+    assert math.isclose(z, 1.0, rel_tol=REL)
+    # one observed leaf: P(e) from the CPTs' own chain rule is not available in closed form, but
+    # P(x=0) + P(x=1) must be 1
+    leaf = bn.nvars - 1
+    z0, _ = bn.partition({leaf: 0}, "mf")
+    z1, _ = bn.partition({leaf: 1}, "mf")
+    assert math.isclose(z0 + z1, 1.0, rel_tol=REL)
+    bn.close()
