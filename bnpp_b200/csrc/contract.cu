@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "common.cuh"
@@ -241,6 +242,67 @@ __global__ void __launch_bounds__(kBlock) contract_fast(const __grid_constant__ 
     grid_sum_to(zacc, h.partials, h.ticket, h.z);
 }
 
+// Power-of-two iteration space, the hot variant.  A CTA owns chunks of CH = U * kBlock
+// consecutive items (CH a power of two, dividing n_items).  Because offsets are sums of
+// bit-fields of the item index and  item = chunk_base + (u * kBlock + tid)  has disjoint
+// bits in its two terms,  off(item) = off(chunk_base) + off(u * kBlock + tid)  exactly:
+// the second term is loop-invariant per thread, the first is computed once per chunk
+// (uniform over the CTA) and shared by the U items -- U-fold less index arithmetic.
+template <int K, int C, int V, int U, bool DIV>
+__global__ void __launch_bounds__(kBlock) contract_fast_p2s(const __grid_constant__ ParamsP2 p)
+{
+    const ParamsHead &h = p.h;
+    constexpr uint32_t CH = U * kBlock;
+    uint32_t lo[U][K], olo[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) decompose<K>(p, threadIdx.x + u * kBlock, lo[u], olo[u]);
+    const uint32_t n_chunks = (uint32_t)(h.n_items / CH);
+    double zacc = 0.0;
+    bool zero_div = false;
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        uint32_t hi[K], ohi;
+        decompose<K>(p, c * CH, hi, ohi);
+        double raw[U][K][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) raw[u][k][e] = 0.0;
+                issue_loads<C, V>(h.in[k] + (hi[k] + lo[u][k]), h.sx[k], h.sl[k], h.cls[k], raw[u][k]);
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double r[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+#pragma unroll
+                for (int x = 0; x < C; ++x) {
+                    double a = pick(raw[u][0], h.cls[0], j, x);
+#pragma unroll
+                    for (int k = 1; k < K; ++k) {
+                        const double t = pick(raw[u][k], h.cls[k], j, x);
+                        if (DIV) { zero_div |= (t == 0.0); a = __ddiv_rn(a, t); }
+                        else a = __dmul_rn(a, t);
+                    }
+                    r[j] = (x == 0) ? a : __dadd_rn(r[j], a);
+                }
+            }
+            double *o = h.out + (ohi + olo[u]);
+            if (V == 2) {
+                zacc = __dadd_rn(zacc, __dadd_rn(r[0], r[V - 1]));
+                if (h.out_vec) *reinterpret_cast<double2 *>(o) = make_double2(r[0], r[V - 1]);
+                else { o[0] = r[0]; o[h.sol] = r[V - 1]; }
+            } else {
+                zacc = __dadd_rn(zacc, r[0]);
+                o[0] = r[0];
+            }
+        }
+    }
+    if (DIV && zero_div) atomicOr(h.status, BNPP_STATUS_ZERO_DIVISOR);
+    grid_sum_to(zacc, h.partials, h.ticket, h.z);
+}
+
 // Generic path: any cardinality of the eliminated variable, one output entry per item.
 template <class P, int K, bool DIV>
 __global__ void __launch_bounds__(kBlock) contract_generic(const __grid_constant__ P p)
@@ -332,25 +394,89 @@ static uint32_t ilog2(uint32_t v) { uint32_t l = 0; while ((1u << l) < v) ++l; r
 constexpr uint64_t kTileOutputs = 1u << 13;     // the output's fastest axes covering this many entries keep their order
 constexpr uint64_t kReuseBytes = 32ull << 20;   // operands above this do not survive in L2 between passes
 
+typedef void (*p2s_fn)(const ParamsP2);
+
+template <int K, int U>
+static p2s_fn p2s_fast(int C, int V)
+{
+    if (C == 1) return V == 2 ? contract_fast_p2s<K, 1, 2, U, false> : contract_fast_p2s<K, 1, 1, U, false>;
+    return V == 2 ? contract_fast_p2s<K, 2, 2, U, false> : contract_fast_p2s<K, 2, 1, U, false>;
+}
+
+static p2s_fn pick_p2s(int K, int C, int V, bool div, int &U)
+{
+    if (div) {
+        U = 4;
+        if (C == 1) return V == 2 ? contract_fast_p2s<2, 1, 2, 4, true> : contract_fast_p2s<2, 1, 1, 4, true>;
+        return V == 2 ? contract_fast_p2s<2, 2, 2, 4, true> : contract_fast_p2s<2, 2, 1, 4, true>;
+    }
+    switch (K) {
+    case 1: U = 4; return p2s_fast<1, 4>(C, V);
+    case 2: U = 4; return p2s_fast<2, 4>(C, V);
+    case 3: U = 2; return p2s_fast<3, 2>(C, V);
+    case 4: U = 2; return p2s_fast<4, 2>(C, V);
+    case 5: U = 2; return p2s_fast<5, 2>(C, V);
+    default: U = 2; return p2s_fast<6, 2>(C, V);
+    }
+}
+
+// persistent grid: as many CTAs as are co-resident (occupancy is register-bound and differs per variant)
+template <class F>
+static uint64_t resident_ctas(bnpp_ctx *ctx, F fn)
+{
+    static std::map<const void *, int> cache;
+    const void *key = reinterpret_cast<const void *>(fn);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        it = cache.insert({key, per_sm}).first;
+    }
+    return (uint64_t)ctx->sm_count * it->second;
+}
+
+static void note_launch(bnpp_ctx *ctx, const ParamsHead &h, const char *variant, int k, int C, int V, int U, bool div,
+                        bool generic, uint32_t R, uint64_t blocks)
+{
+    ctx->launches++;
+    char nm[128];
+    if (generic) snprintf(nm, sizeof nm, "contract_generic<%s,K=%d,div=%d> cx=%u R=%u", variant, k, div, h.cx, R);
+    else snprintf(nm, sizeof nm, "contract_fast<%s,K=%d,C=%d,V=%d,U=%d,div=%d> R=%u cls=%d,%d,%d", variant, k, C, V, U, div, R,
+                  h.cls[0], k > 1 ? h.cls[1] : -1, k > 2 ? h.cls[2] : -1);
+    ctx->last_kernel = nm;
+    ctx->last_grid = (uint32_t)blocks;
+    ctx->last_block = kBlock;
+}
+
 template <class P>
 static int launch(bnpp_ctx *ctx, P &p, int k, int C, int V, bool div, bool generic, const char *mode, uint32_t R)
 {
     int U = 1;
     typename Launch<P>::fn_t fn = Launch<P>::pick(k, C, V, div, generic, U);
     uint64_t blocks = (p.h.n_items + (uint64_t)kBlock * U - 1) / ((uint64_t)kBlock * U);
-    const uint64_t cap = (uint64_t)ctx->sm_count * 8;   // persistent grid: up to 8 CTAs of 256 threads per SM
+    const uint64_t cap = resident_ctas(ctx, fn);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     fn<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(p);
     BNPP_CUDA(ctx, cudaGetLastError());
-    ctx->launches++;
-    char nm[128];
-    if (generic) snprintf(nm, sizeof nm, "contract_generic<%s,K=%d,div=%d> cx=%u R=%u", mode, k, div, p.h.cx, R);
-    else snprintf(nm, sizeof nm, "contract_fast<%s,K=%d,C=%d,V=%d,U=%d,div=%d> R=%u cls=%d,%d,%d", mode, k, C, V, U, div, R,
-                  p.h.cls[0], k > 1 ? p.h.cls[1] : -1, k > 2 ? p.h.cls[2] : -1);
-    ctx->last_kernel = nm;
-    ctx->last_grid = (uint32_t)blocks;
-    ctx->last_block = kBlock;
+    note_launch(ctx, p.h, mode, k, C, V, U, div, generic, R, blocks);
+    return BNPP_OK;
+}
+
+static int launch_p2s(bnpp_ctx *ctx, ParamsP2 &p, int k, int C, int V, bool div, uint32_t R, bool &done)
+{
+    int U = 1;
+    p2s_fn fn = pick_p2s(k, C, V, div, U);
+    const uint64_t ch = (uint64_t)kBlock * U;
+    done = false;
+    if (p.h.n_items < ch || p.h.n_items % ch) return BNPP_OK;   // tiny problem: per-item kernel
+    uint64_t blocks = p.h.n_items / ch;
+    const uint64_t cap = resident_ctas(ctx, fn);
+    if (blocks > cap) blocks = cap;
+    fn<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(p);
+    BNPP_CUDA(ctx, cudaGetLastError());
+    note_launch(ctx, p.h, "p2s", k, C, V, U, div, false, R, blocks);
+    done = true;
     return BNPP_OK;
 }
 
@@ -542,6 +668,11 @@ int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *ou
                 else p.f[q][nf++] = Field{(cur_bits >= 32) ? 0xffffffffu : ((1u << cur_bits) - 1), (uint32_t)cur_mul, cur_sh};
             }
             p.nf[q] = (uint8_t)nf;
+        }
+        if (fits && !generic) {
+            bool done = false;
+            const int rc = launch_p2s(ctx, p, k, C, V, divide != 0, R, done);
+            if (rc != BNPP_OK || done) return rc;
         }
         if (fits) return launch(ctx, p, k, C, V, divide != 0, generic, "p2", R);
     }

@@ -56,6 +56,7 @@ struct bnpp_ve_plan {
     bool profiling = false;
     std::vector<cudaEvent_t> ev;
     std::vector<float> step_ms;
+    std::vector<std::string> step_kernel;
 };
 
 using namespace bnpp;
@@ -283,6 +284,15 @@ int bnpp_ve_plan_step_stats(bnpp_ve_plan *pl, uint64_t n, float *ms, uint64_t *b
     return BNPP_OK;
 }
 
+int bnpp_ve_plan_step_kernel(const bnpp_ve_plan *pl, uint64_t step, char *name, size_t name_len)
+{
+    if (!pl || !name || !name_len) return BNPP_EINVAL;
+    const std::string s = step < pl->step_kernel.size() ? pl->step_kernel[step] : std::string();
+    strncpy(name, s.c_str(), name_len - 1);
+    name[name_len - 1] = 0;
+    return BNPP_OK;
+}
+
 int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const uint32_t *obs_val, double *result_dev,
                      double *z_dev)
 {
@@ -334,6 +344,10 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             ptr[st.out] = dst;
         }
         rc = contract(ctx, (int)st.operands.size(), ops, &os, st.elim, 0, dst, st.out == -2 ? z_dev : nullptr);
+        if (pl->profiling) {
+            pl->step_kernel.resize(pl->steps.size());
+            pl->step_kernel[s] = ctx->last_kernel;
+        }
         for (int id : st.operands)
             if (owned[id] && pl->f[id].last_use == (int)s) {
                 bnpp_free(ctx, owned[id]);

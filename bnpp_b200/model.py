@@ -33,6 +33,7 @@ def _declare(L):
     L.bnpp_ve_plan_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.bnpp_ve_plan_step_stats.argtypes = [ctypes.c_void_p, ctypes.c_uint64, P(ctypes.c_float), capi.c_u64p, capi.c_u64p,
                                           P(ctypes.c_int32)]
+    L.bnpp_ve_plan_step_kernel.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_size_t]
     L._ve_declared = True
 
 
@@ -121,7 +122,12 @@ class VEPlan:
         k = (ctypes.c_int32 * max(1, n))()
         self.ctx.check(self.ctx.L.bnpp_ve_plan_step_stats(self.h, n, ms, ctypes.cast(by, capi.c_u64p),
                                                           ctypes.cast(en, capi.c_u64p), k))
-        return [{"ms": ms[i], "bytes": by[i], "entries": en[i], "k": k[i]} for i in range(n)]
+        out = []
+        buf = ctypes.create_string_buffer(160)
+        for i in range(n):
+            self.ctx.L.bnpp_ve_plan_step_kernel(self.h, i, buf, 160)
+            out.append({"ms": ms[i], "bytes": by[i], "entries": en[i], "k": k[i], "kernel": buf.value.decode()})
+        return out
 
     def close(self):
         if self.h:

@@ -168,6 +168,8 @@ int bnpp_ve_plan_run(bnpp_ve_plan *plan, const double *const *tables_dev, const 
  * ms / algorithmic bytes / union entries / operand count per launch (synchronises). */
 int bnpp_ve_plan_set_profiling(bnpp_ve_plan *plan, int on);
 int bnpp_ve_plan_step_stats(bnpp_ve_plan *plan, uint64_t n, float *ms, uint64_t *bytes, uint64_t *entries, int32_t *k);
+/* kernel variant the last profiled run used for launch `step` (diagnostics) */
+int bnpp_ve_plan_step_kernel(const bnpp_ve_plan *plan, uint64_t step, char *name, size_t name_len);
 
 /* ---- factor-graph sum-product (K7), code/graph.cpp:256-403 --------------------- */
 typedef struct bnpp_fg bnpp_fg;
