@@ -303,6 +303,56 @@ __global__ void __launch_bounds__(kBlock) contract_fast_p2s(const __grid_constan
     grid_sum_to(zacc, h.partials, h.ticket, h.z);
 }
 
+// The variable-elimination hot variant.  With the canonical axis order of ve.cu every
+// operand of a bucket has the eliminated (binary) variable as its fastest axis, so an
+// operand's micro-tile is either 4 contiguous doubles (it also has the output's fastest
+// axis: one 32-byte load) or 2 contiguous doubles shared by both output entries (one
+// 16-byte load).  Which of the two is a compile-time bit of MASK: no class dispatch, no
+// register shuffling -- per item K loads, 4(K-1) multiplies, 2+1 adds, one 16-byte store.
+template <int K, unsigned MASK, int U>
+__global__ void __launch_bounds__(kBlock) contract_canon(const __grid_constant__ ParamsP2 p)
+{
+    const ParamsHead &h = p.h;
+    constexpr uint32_t CH = U * kBlock;
+    uint32_t lo[U][K], olo[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) decompose<K>(p, threadIdx.x + u * kBlock, lo[u], olo[u]);
+    const uint32_t n_chunks = (uint32_t)(h.n_items / CH);
+    double zacc = 0.0;
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        uint32_t hi[K], ohi;
+        decompose<K>(p, c * CH, hi, ohi);
+        double4_t t[U][K];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double *src = h.in[k] + (hi[k] + lo[u][k]);
+                if ((MASK >> k) & 1u) {
+                    t[u][k] = ld4(src);
+                } else {
+                    const double2 v = ld2(src);
+                    t[u][k].x = v.x; t[u][k].y = v.y; t[u][k].z = v.x; t[u][k].w = v.y;
+                }
+            }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double a = t[u][0].x, b = t[u][0].y, cc = t[u][0].z, d = t[u][0].w;
+#pragma unroll
+            for (int k = 1; k < K; ++k) {
+                a = __dmul_rn(a, t[u][k].x);
+                b = __dmul_rn(b, t[u][k].y);
+                cc = __dmul_rn(cc, t[u][k].z);
+                d = __dmul_rn(d, t[u][k].w);
+            }
+            const double r0 = __dadd_rn(a, b), r1 = __dadd_rn(cc, d);
+            zacc = __dadd_rn(zacc, __dadd_rn(r0, r1));
+            *reinterpret_cast<double2 *>(h.out + (ohi + olo[u])) = make_double2(r0, r1);
+        }
+    }
+    grid_sum_to(zacc, h.partials, h.ticket, h.z);
+}
+
 // Generic path: any cardinality of the eliminated variable, one output entry per item.
 template <class P, int K, bool DIV>
 __global__ void __launch_bounds__(kBlock) contract_generic(const __grid_constant__ P p)
@@ -396,6 +446,28 @@ constexpr uint64_t kReuseBytes = 32ull << 20;   // operands above this do not su
 
 typedef void (*p2s_fn)(const ParamsP2);
 
+constexpr int kCanonU = 4;
+static p2s_fn pick_canon(int K, unsigned mask)
+{
+    switch (K * 8 + (int)mask) {
+    case 1 * 8 + 0: return contract_canon<1, 0, kCanonU>;
+    case 1 * 8 + 1: return contract_canon<1, 1, kCanonU>;
+    case 2 * 8 + 0: return contract_canon<2, 0, kCanonU>;
+    case 2 * 8 + 1: return contract_canon<2, 1, kCanonU>;
+    case 2 * 8 + 2: return contract_canon<2, 2, kCanonU>;
+    case 2 * 8 + 3: return contract_canon<2, 3, kCanonU>;
+    case 3 * 8 + 0: return contract_canon<3, 0, kCanonU>;
+    case 3 * 8 + 1: return contract_canon<3, 1, kCanonU>;
+    case 3 * 8 + 2: return contract_canon<3, 2, kCanonU>;
+    case 3 * 8 + 3: return contract_canon<3, 3, kCanonU>;
+    case 3 * 8 + 4: return contract_canon<3, 4, kCanonU>;
+    case 3 * 8 + 5: return contract_canon<3, 5, kCanonU>;
+    case 3 * 8 + 6: return contract_canon<3, 6, kCanonU>;
+    case 3 * 8 + 7: return contract_canon<3, 7, kCanonU>;
+    default: return nullptr;
+    }
+}
+
 template <int K, int U>
 static p2s_fn p2s_fast(int C, int V)
 {
@@ -466,7 +538,23 @@ static int launch(bnpp_ctx *ctx, P &p, int k, int C, int V, bool div, bool gener
 static int launch_p2s(bnpp_ctx *ctx, ParamsP2 &p, int k, int C, int V, bool div, uint32_t R, bool &done)
 {
     int U = 1;
-    p2s_fn fn = pick_p2s(k, C, V, div, U);
+    p2s_fn fn = nullptr;
+    const char *variant = "p2s";
+    // canonical VE layout: every operand has the eliminated variable as its stride-1 axis
+    if (!div && C == 2 && V == 2 && k <= 3 && p.h.out_vec) {
+        unsigned mask = 0;
+        bool canon = true;
+        for (int q = 0; q < k; ++q) {
+            if (p.h.cls[q] == LC_V4) mask |= 1u << q;
+            else if (p.h.cls[q] != LC_VX_B) canon = false;
+        }
+        if (canon) {
+            fn = pick_canon(k, mask);
+            U = kCanonU;
+            variant = "canon";
+        }
+    }
+    if (!fn) fn = pick_p2s(k, C, V, div, U);
     const uint64_t ch = (uint64_t)kBlock * U;
     done = false;
     if (p.h.n_items < ch || p.h.n_items % ch) return BNPP_OK;   // tiny problem: per-item kernel
@@ -475,7 +563,7 @@ static int launch_p2s(bnpp_ctx *ctx, ParamsP2 &p, int k, int C, int V, bool div,
     if (blocks > cap) blocks = cap;
     fn<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(p);
     BNPP_CUDA(ctx, cudaGetLastError());
-    note_launch(ctx, p.h, "p2s", k, C, V, U, div, false, R, blocks);
+    note_launch(ctx, p.h, variant, k, C, V, U, div, false, R, blocks);
     done = true;
     return BNPP_OK;
 }

@@ -114,6 +114,50 @@ int add_step(bnpp_ve_plan *pl, std::vector<int> ops, int64_t elim, const std::ma
     return st.out;
 }
 
+uint64_t union_size(const bnpp_ve_plan *pl, const std::vector<int> &ops)
+{
+    std::map<uint32_t, uint32_t> u;
+    for (int id : ops)
+        for (size_t i = 0; i < pl->f[id].var.size(); ++i) u[pl->f[id].var[i]] = pl->f[id].card[i];
+    uint64_t n = 1;
+    for (auto &e : u) n *= e.second;
+    return n;
+}
+
+// A bucket that streams a wide table usually also holds a handful of small CPTs.  Gathering
+// from each of them costs instructions per entry of the WIDE table; multiplying them into
+// one small (L2-resident) table first costs a negligible launch and leaves the streaming
+// kernel with the wide operand(s) plus one small one (K <= 3: the `canon` variant).
+constexpr uint64_t kWideEntries = 1ull << 20;
+void fold_small(bnpp_ve_plan *pl, std::vector<int> &ops, const std::map<uint32_t, uint64_t> &rank)
+{
+    if (ops.size() < 2) return;
+    std::stable_sort(ops.begin(), ops.end(), [pl](int a, int b) { return pl->f[a].size < pl->f[b].size; });
+    const uint64_t big = pl->f[ops.back()].size;
+    if (big < kWideEntries) return;
+    const uint64_t cap = std::max<uint64_t>(1ull << 12, big >> 4);
+    // longest prefix (smallest operands) whose joint table stays small
+    size_t m = 0;
+    while (m < ops.size() - 1) {
+        std::vector<int> head(ops.begin(), ops.begin() + m + 1);
+        if (pl->f[ops[m]].size > cap || union_size(pl, head) > cap) break;
+        ++m;
+    }
+    // a lone small operand is folded (= copied into canonical axis order) only when it is a
+    // raw input view, whose file-order layout would otherwise force scalar gathers
+    if (m == 0 || (m == 1 && pl->f[ops[0]].src < 0)) return;
+    std::vector<int> work(ops.begin(), ops.begin() + m);
+    while ((int)work.size() > kMaxK) {
+        std::vector<int> part(work.begin(), work.begin() + kMaxK);
+        const int t = add_step(pl, part, -1, rank, false);
+        work.erase(work.begin(), work.begin() + kMaxK);
+        work.insert(work.begin(), t);
+    }
+    const int t = add_step(pl, work, -1, rank, false);
+    ops.erase(ops.begin(), ops.begin() + m);
+    ops.insert(ops.begin(), t);
+}
+
 // the kernel takes at most BNPP_MAX_OPERANDS tables: fold the smallest ones first
 void shrink(bnpp_ve_plan *pl, std::vector<int> &ops, const std::map<uint32_t, uint64_t> &rank)
 {
@@ -197,6 +241,7 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
     for (int i = 0; i < n_order; ++i) {
         std::vector<int> ops = bucket[i];
         if (ops.empty()) continue;    // the reference makes a scalar 1 here; multiplying by it changes nothing
+        fold_small(pl, ops, rank);
         shrink(pl, ops, rank);
         const int t = add_step(pl, ops, (int64_t)order[i], rank, false);
         pl->union_entries += pl->steps.back().union_entries;
