@@ -1,0 +1,117 @@
+#include "io.hh"
+
+#include <iostream>
+
+namespace bn {
+
+namespace {
+
+// next whitespace-separated token; a token starting with '#' comments out the rest of its line
+// (code/io.cpp:14-23)
+bool next_token(std::ifstream &in, std::string &tok)
+{
+    while (in >> tok) {
+        if (tok[0] != '#') return true;
+        std::getline(in, tok);
+    }
+    return false;
+}
+
+unsigned next_unsigned(std::ifstream &in)
+{
+    std::string tok;
+    return next_token(in, tok) ? (unsigned)std::stoi(tok) : 0u;
+}
+
+double next_double(std::ifstream &in)
+{
+    std::string tok;
+    return next_token(in, tok) ? std::stod(tok) : 0.0;
+}
+
+template <class M>
+int load(std::string &filename, M **model, const char *want, const char *other)
+{
+    std::ifstream in(filename);
+    if (!in.is_open()) {
+        std::cerr << "Error: couldn't read file " << filename << std::endl;
+        return -1;
+    }
+    const std::string type = read_file_header(in);
+    if (type == other) {
+        // checked BEFORE building anything: the reference builds first and leaks (SURVEY A.2 v)
+        std::cerr << "Error: file " << filename << " is not a " << want << " net." << std::endl;
+        return -2;
+    }
+    std::vector<Variable*> variables;
+    std::vector<Factor*> factors;
+    read_variables(in, variables);
+    read_factors(in, variables, factors);
+    if (type == want) *model = new M(filename, variables, factors);
+    return 0;
+}
+
+}  // namespace
+
+std::string read_file_header(std::ifstream &in)
+{
+    std::string tok;
+    next_token(in, tok);
+    if (tok != "BAYES" && tok != "MARKOV")
+        std::cerr << "ERROR! Expected 'BAYES' or 'MARKOV' file header, found: " << tok << std::endl;
+    return tok;
+}
+
+void read_variables(std::ifstream &in, std::vector<Variable*> &variables)
+{
+    const unsigned n = next_unsigned(in);
+    for (unsigned id = 0; id < n; ++id) variables.push_back(new Variable(id, next_unsigned(in)));
+}
+
+// scopes first, then the tables; each factor's partition is summed in file order (code/io.cpp:66-100)
+void read_factors(std::ifstream &in, std::vector<Variable*> &variables, std::vector<Factor*> &factors)
+{
+    const unsigned n = next_unsigned(in);
+    std::vector<Domain*> domains;
+    for (unsigned i = 0; i < n; ++i) {
+        const unsigned width = next_unsigned(in);
+        std::vector<const Variable*> scope;
+        for (unsigned j = 0; j < width; ++j) scope.push_back(variables[next_unsigned(in)]);
+        domains.push_back(new Domain(scope));
+    }
+    for (unsigned i = 0; i < n; ++i) {
+        const unsigned size = next_unsigned(in);
+        std::vector<double> values;
+        values.reserve(size);
+        double partition = 0;
+        for (unsigned j = 0; j < size; ++j) {
+            values.push_back(next_double(in));
+            partition += values.back();
+        }
+        factors.push_back(new Factor(domains[i], values, partition));
+    }
+}
+
+int read_uai_model(std::string &filename, BN **model) { return load(filename, model, "BAYES", "MARKOV"); }
+
+int read_uai_model(std::string &filename, MN **model) { return load(filename, model, "MARKOV", "BAYES"); }
+
+// only a leading sample count of exactly 1 is honoured (code/io.cpp:157-180, SURVEY A.2 iv)
+int read_uai_evidence(std::string &filename, std::unordered_map<unsigned,unsigned> &evidence)
+{
+    std::ifstream in(filename);
+    if (!in.is_open()) {
+        std::cerr << "Error: couldn't read file " << filename << std::endl;
+        return -1;
+    }
+    if (next_unsigned(in) == 1) {
+        const unsigned k = next_unsigned(in);
+        for (unsigned i = 0; i < k; ++i) {
+            const unsigned id = next_unsigned(in);
+            evidence[id] = next_unsigned(in);
+        }
+    }
+    return 0;
+}
+
+}  // namespace bn

@@ -1,0 +1,39 @@
+#include "runtime.hh"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace bn {
+namespace gpu {
+
+static bnpp_ctx *g_ctx = nullptr;
+
+bnpp_ctx *ctx()
+{
+    if (!g_ctx) {
+        const char *dev = std::getenv("BNPP_DEVICE");
+        const int rc = bnpp_ctx_create(dev ? std::atoi(dev) : 0, nullptr, &g_ctx);
+        if (rc != BNPP_OK) {
+            std::fprintf(stderr, "bn-pp (B200 build): cannot create a CUDA context: %s\n", bnpp_last_error(nullptr));
+            std::exit(3);
+        }
+        std::atexit(shutdown);
+    }
+    return g_ctx;
+}
+
+void check(int rc, const char *what)
+{
+    if (rc == BNPP_OK) return;
+    std::fprintf(stderr, "bn-pp (B200 build): %s failed (%d): %s\n", what, rc, bnpp_last_error(g_ctx));
+    std::exit(4);
+}
+
+void shutdown()
+{
+    if (g_ctx) bnpp_ctx_destroy(g_ctx);
+    g_ctx = nullptr;
+}
+
+}  // namespace gpu
+}  // namespace bn
