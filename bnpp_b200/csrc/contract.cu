@@ -309,7 +309,9 @@ __global__ void __launch_bounds__(kBlock) contract_fast_p2s(const __grid_constan
 // axis: one 32-byte load) or 2 contiguous doubles shared by both output entries (one
 // 16-byte load).  Which of the two is a compile-time bit of MASK: no class dispatch, no
 // register shuffling -- per item K loads, 4(K-1) multiplies, 2+1 adds, one 16-byte store.
-template <int K, unsigned MASK, int U>
+// INVK >= 0 names an operand that does not depend on the two axes the plan placed at the
+// thread's unroll bits: its micro-tile is loaded once and reused for all U items.
+template <int K, unsigned MASK, int U, int INVK>
 __global__ void __launch_bounds__(kBlock) contract_canon(const __grid_constant__ ParamsP2 p)
 {
     const ParamsHead &h = p.h;
@@ -327,6 +329,7 @@ __global__ void __launch_bounds__(kBlock) contract_canon(const __grid_constant__
         for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int k = 0; k < K; ++k) {
+                if (k == INVK && u > 0) continue;   // same element for all U items: loaded once, kept in registers
                 const double *src = h.in[k] + (hi[k] + lo[u][k]);
                 if ((MASK >> k) & 1u) {
                     t[u][k] = ld4(src);
@@ -337,13 +340,15 @@ __global__ void __launch_bounds__(kBlock) contract_canon(const __grid_constant__
             }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            double a = t[u][0].x, b = t[u][0].y, cc = t[u][0].z, d = t[u][0].w;
+            const double4_t &t0 = t[INVK == 0 ? 0 : u][0];
+            double a = t0.x, b = t0.y, cc = t0.z, d = t0.w;
 #pragma unroll
             for (int k = 1; k < K; ++k) {
-                a = __dmul_rn(a, t[u][k].x);
-                b = __dmul_rn(b, t[u][k].y);
-                cc = __dmul_rn(cc, t[u][k].z);
-                d = __dmul_rn(d, t[u][k].w);
+                const double4_t &tk = t[INVK == k ? 0 : u][k];
+                a = __dmul_rn(a, tk.x);
+                b = __dmul_rn(b, tk.y);
+                cc = __dmul_rn(cc, tk.z);
+                d = __dmul_rn(d, tk.w);
             }
             const double r0 = __dadd_rn(a, b), r1 = __dadd_rn(cc, d);
             zacc = __dadd_rn(zacc, __dadd_rn(r0, r1));
@@ -447,23 +452,35 @@ constexpr uint64_t kReuseBytes = 32ull << 20;   // operands above this do not su
 typedef void (*p2s_fn)(const ParamsP2);
 
 constexpr int kCanonU = 4;
-static p2s_fn pick_canon(int K, unsigned mask)
+
+template <int K, unsigned MASK>
+static p2s_fn canon_inv(int invk)
+{
+    switch (invk) {
+    case 0: return contract_canon<K, MASK, kCanonU, 0>;
+    case 1: return K > 1 ? contract_canon<K, MASK, kCanonU, (K > 1 ? 1 : -1)> : nullptr;
+    case 2: return K > 2 ? contract_canon<K, MASK, kCanonU, (K > 2 ? 2 : -1)> : nullptr;
+    default: return contract_canon<K, MASK, kCanonU, -1>;
+    }
+}
+
+static p2s_fn pick_canon(int K, unsigned mask, int invk)
 {
     switch (K * 8 + (int)mask) {
-    case 1 * 8 + 0: return contract_canon<1, 0, kCanonU>;
-    case 1 * 8 + 1: return contract_canon<1, 1, kCanonU>;
-    case 2 * 8 + 0: return contract_canon<2, 0, kCanonU>;
-    case 2 * 8 + 1: return contract_canon<2, 1, kCanonU>;
-    case 2 * 8 + 2: return contract_canon<2, 2, kCanonU>;
-    case 2 * 8 + 3: return contract_canon<2, 3, kCanonU>;
-    case 3 * 8 + 0: return contract_canon<3, 0, kCanonU>;
-    case 3 * 8 + 1: return contract_canon<3, 1, kCanonU>;
-    case 3 * 8 + 2: return contract_canon<3, 2, kCanonU>;
-    case 3 * 8 + 3: return contract_canon<3, 3, kCanonU>;
-    case 3 * 8 + 4: return contract_canon<3, 4, kCanonU>;
-    case 3 * 8 + 5: return contract_canon<3, 5, kCanonU>;
-    case 3 * 8 + 6: return contract_canon<3, 6, kCanonU>;
-    case 3 * 8 + 7: return contract_canon<3, 7, kCanonU>;
+    case 1 * 8 + 0: return canon_inv<1, 0>(-1);
+    case 1 * 8 + 1: return canon_inv<1, 1>(-1);
+    case 2 * 8 + 0: return canon_inv<2, 0>(invk);
+    case 2 * 8 + 1: return canon_inv<2, 1>(invk);
+    case 2 * 8 + 2: return canon_inv<2, 2>(invk);
+    case 2 * 8 + 3: return canon_inv<2, 3>(invk);
+    case 3 * 8 + 0: return canon_inv<3, 0>(invk);
+    case 3 * 8 + 1: return canon_inv<3, 1>(invk);
+    case 3 * 8 + 2: return canon_inv<3, 2>(invk);
+    case 3 * 8 + 3: return canon_inv<3, 3>(invk);
+    case 3 * 8 + 4: return canon_inv<3, 4>(invk);
+    case 3 * 8 + 5: return canon_inv<3, 5>(invk);
+    case 3 * 8 + 6: return canon_inv<3, 6>(invk);
+    case 3 * 8 + 7: return canon_inv<3, 7>(invk);
     default: return nullptr;
     }
 }
@@ -549,9 +566,18 @@ static int launch_p2s(bnpp_ctx *ctx, ParamsP2 &p, int k, int C, int V, bool div,
             else if (p.h.cls[q] != LC_VX_B) canon = false;
         }
         if (canon) {
-            fn = pick_canon(k, mask);
+            // an operand none of whose bit-fields touches item bits 8..9 (= u * kBlock) is the
+            // same element for all U items of a thread; keep the heaviest such operand in registers
+            int invk = -1;
+            for (int q = 0; q < k; ++q) {
+                bool touches = false;
+                for (int f = 0; f < (int)p.nf[q]; ++f)
+                    touches |= (((uint64_t)p.f[q][f].mask << p.f[q][f].sh) & (uint64_t)(kBlock * (kCanonU - 1))) != 0;
+                if (!touches && (invk < 0 || (((mask >> q) & 1u) && !((mask >> invk) & 1u)))) invk = q;
+            }
+            fn = pick_canon(k, mask, invk);
             U = kCanonU;
-            variant = "canon";
+            variant = invk < 0 ? "canon" : (invk == 0 ? "canon/inv0" : (invk == 1 ? "canon/inv1" : "canon/inv2"));
         }
     }
     if (!fn) fn = pick_p2s(k, C, V, div, U);
@@ -645,6 +671,48 @@ int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *ou
         }
         if (any)
             std::stable_sort(it.begin(), it.begin() + first_tile, [](const Axis &x, const Axis &y) { return x.miss < y.miss; });
+    }
+
+    // The U items of a thread differ in item bits 8.. (u * kBlock).  Put there binary axes
+    // that operands LACK: those operands then address the same element for several of the
+    // thread's items, and the repeated loads merge in L1 instead of each crossing L2 (an
+    // L2-resident broadcast operand costs L2 bandwidth like a streamed one).
+    if (cx <= 2) {
+        size_t split = it.size();
+        uint64_t inner = 1;
+        while (split > 0 && inner < 2u * kBlock) inner *= it[--split].ext;
+        bool p2all = true;
+        for (const Axis &a : it) p2all = p2all && is_pow2(a.ext);
+        if (p2all && inner == 2u * kBlock && split > 0) {
+            auto weight = [&](int q) { return (uint64_t)(sx[q] ? 2 : 1) * (it.back().s[q] ? 2 : 1); };
+            auto score = [&](size_t a) {
+                uint64_t sc = 0;
+                for (int q = 0; q < k; ++q)
+                    if (it[a].s[q] == 0) sc += weight(q);
+                return sc;
+            };
+            // the heaviest operand that lacks at least two eligible axes gets both unroll bits
+            int owner = -1;
+            for (int q = 0; q < k; ++q) {
+                int lacking = 0;
+                for (size_t a = 0; a < split; ++a) lacking += (it[a].ext == 2 && it[a].s[q] == 0);
+                if (lacking >= 2 && (owner < 0 || weight(q) > weight(owner))) owner = q;
+            }
+            for (int pick = 0; pick < 2; ++pick) {
+                int best = -1;
+                uint64_t best_score = 0;
+                for (size_t a = 0; a + pick < split; ++a) {
+                    if (it[a].ext != 2) continue;
+                    if (owner >= 0 && it[a].s[owner] != 0) continue;
+                    const uint64_t sc = score(a);
+                    if (sc > best_score) { best_score = sc; best = (int)a; }
+                }
+                if (best < 0) break;
+                const Axis ax = it[best];   // move it to just above the thread bits (and the axis placed before it)
+                it.erase(it.begin() + best);
+                it.insert(it.begin() + (split - 1 - pick), ax);
+            }
+        }
     }
 
     // merge neighbours that are contiguous in the output and in every operand

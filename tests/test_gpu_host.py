@@ -111,26 +111,30 @@ def test_query_ve(files, golden_models):
 
 def test_factor_ops_through_cpp_api(golden_ops):
     """bn::Factor product / divide / sum_out / conditioning / normalize / max / min as the reference's
-    callers use them (code/factor.hh:36-44), against the reference's own dumps: values bit-exact"""
-    for c in golden_ops[:40]:
-        cards = c["cards"]
-        def fac(nm, rec):
-            return "factor %s %d %s %s" % (nm, len(rec["scope"]), " ".join(map(str, rec["scope"])),
-                                           " ".join("%.17g" % v for v in rec["values"]))
-        ev = c["evidence"]
-        script = ["vars %d %s" % (len(cards), " ".join(map(str, cards))), fac("a", c["a"]), fac("b", c["b"]),
-                  "product a b p", "dump p", "divide a b q", "dump q", "sumout p %d s" % c["sum_var"], "dump s",
-                  "cond p c %d %s" % (len(ev), " ".join("%s %s" % kv for kv in sorted(ev.items()))), "dump c",
-                  "normalize p n", "dump n", "max p", "min p"]
-        rows = run_harness(script)
-        facs = orc.RefHarness.factors(rows)
-        for (scope, size, z, vals), nm in zip(facs, ["p", "q", "s", "c"]):
+    callers use them (code/factor.hh:36-44), against the reference's own dumps: values bit-exact.
+    One harness process runs all cases (CUDA context creation dominates a process's life)."""
+    def fac(nm, rec):
+        return "factor %s %d %s %s" % (nm, len(rec["scope"]), " ".join(map(str, rec["scope"])),
+                                       " ".join("%.17g" % v for v in rec["values"]))
+    cases = golden_ops[:60]
+    script = []
+    for c in cases:
+        cards, ev = c["cards"], c["evidence"]
+        script += ["vars %d %s" % (len(cards), " ".join(map(str, cards))), fac("a", c["a"]), fac("b", c["b"]),
+                   "product a b p", "dump p", "divide a b q", "dump q", "sumout p %d s" % c["sum_var"], "dump s",
+                   "cond p c %d %s" % (len(ev), " ".join("%s %s" % kv for kv in sorted(ev.items()))), "dump c",
+                   "normalize p n", "dump n", "max p", "min p"]
+    rows = run_harness(script)
+    facs = orc.RefHarness.factors(rows)
+    scal = [float(r[1]) for r in rows if r[0] == "SCALAR"]
+    assert len(facs) == 5 * len(cases) and len(scal) == 2 * len(cases)
+    for i, c in enumerate(cases):
+        for (scope, size, z, vals), nm in zip(facs[5 * i:5 * i + 4], ["p", "q", "s", "c"]):
             assert scope == c[nm]["scope"]
             assert np.array_equal(vals, np.array(c[nm]["values"])), nm
             assert math.isclose(z, c[nm]["partition"], rel_tol=1e-12, abs_tol=1e-300)
-        assert np.allclose(facs[4][3], c["n"]["values"], rtol=1e-12, atol=0.0)
-        sc = [float(r[1]) for r in rows if r[0] == "SCALAR"]
-        assert sc[0] == c["max_p"] and math.isclose(sc[1], c["min_p"], rel_tol=1e-12)
+        assert np.allclose(facs[5 * i + 4][3], c["n"]["values"], rtol=1e-12, atol=0.0)
+        assert scal[2 * i] == c["max_p"] and math.isclose(scal[2 * i + 1], c["min_p"], rel_tol=1e-12)
 
 
 def mask(text):
