@@ -9,6 +9,7 @@
 // fill-in edge insertions see the same element order.  Header-only so the C-ABI
 // library (bnpp_elim_order) and the bn::Graph wrapper share one implementation.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <unordered_map>
 #include <unordered_set>
@@ -169,9 +170,179 @@ public:
         return width;
     }
 
+    const std::vector<unsigned> &cardinalities() const { return card_; }
+
 private:
     std::vector<unsigned> card_;
     Adjacency adj_;
+};
+
+// Same orders as InteractionGraph::ordering, computed faster (once the
+// tables are fast, ordering is what an end-to-end query waits for).
+//
+// What decides the reference's order is (1) the iteration order of the CANDIDATE set --
+// kept here as the very same std::unordered_set<unsigned> with the same insert / erase
+// history -- and (2) per-candidate scores and degrees, which are order-independent sums.
+// The iteration order of the adjacency sets never influences a decision, so adjacency is
+// a bit matrix: fill-in = C(d,2) - (edges inside the neighbourhood) by popcounts, cached
+// per node and recomputed only for nodes whose neighbourhood changed.  Scores wrap modulo
+// 2^32 exactly like the reference's `unsigned` accumulators.
+class FastOrderer {
+public:
+    explicit FastOrderer(const InteractionGraph &g) : card_(g.cardinalities())
+    {
+        unsigned maxid = 0;
+        for (const auto &node : g.adjacency()) {
+            maxid = std::max(maxid, node.first);
+            for (unsigned b : node.second) maxid = std::max(maxid, b);
+        }
+        n_ = maxid + 1;
+        words_ = (n_ + 63) / 64;
+        bits_.assign((size_t)n_ * words_, 0);
+        present_.assign(n_, 0);
+        deg_.assign(n_, 0);
+        for (const auto &node : g.adjacency()) {
+            present_[node.first] = 1;
+            ++alive_;
+            for (unsigned b : node.second) set(node.first, b);
+            deg_[node.first] = (unsigned)node.second.size();
+        }
+        score_.assign(n_, 0);
+        dirty_.assign(n_, 1);
+    }
+
+    std::vector<unsigned> ordering(const std::vector<unsigned> &vars, Heuristic h, unsigned &width)
+    {
+        std::unordered_set<unsigned> cand;
+        for (unsigned v : vars) cand.insert(v);
+        std::vector<unsigned> order;
+        order.reserve(vars.size());
+        width = 0;
+        const bool weighted = (h == H_WEIGHTED_MIN_FILL);
+        while (!cand.empty()) {
+            unsigned best = *cand.begin();
+            if (h == H_MIN_DEGREE) {
+                unsigned best_deg = alive_ + 1;
+                for (unsigned id : cand) {
+                    const unsigned d = degree(id);
+                    if (d < best_deg) { best = id; best_deg = d; }
+                }
+            } else {
+                unsigned best_fill = weighted ? fill(best, true) : alive_ + 1;
+                for (unsigned id : cand) {
+                    const unsigned f = fill(id, weighted);
+                    if (f < best_fill || (f == best_fill && degree(id) < degree(best))) { best = id; best_fill = f; }
+                }
+            }
+            order.push_back(best);
+            const unsigned d = eliminate(best);
+            if (d > width) width = d;
+            cand.erase(best);
+        }
+        return order;
+    }
+
+private:
+    uint64_t *row(unsigned a) { return &bits_[(size_t)a * words_]; }
+    const uint64_t *row(unsigned a) const { return &bits_[(size_t)a * words_]; }
+    void set(unsigned a, unsigned b) { row(a)[b >> 6] |= 1ull << (b & 63); }
+    void clear(unsigned a, unsigned b) { row(a)[b >> 6] &= ~(1ull << (b & 63)); }
+    bool test(unsigned a, unsigned b) const { return (row(a)[b >> 6] >> (b & 63)) & 1ull; }
+    unsigned degree(unsigned id) const { return id < n_ ? deg_[id] : 0; }
+
+    template <class F>
+    void for_each(const uint64_t *r, F f) const
+    {
+        for (unsigned w = 0; w < words_; ++w) {
+            uint64_t x = r[w];
+            while (x) {
+                const unsigned b = (unsigned)__builtin_ctzll(x);
+                x &= x - 1;
+                f(w * 64 + b);
+            }
+        }
+    }
+
+    unsigned fill(unsigned id, bool weighted)
+    {
+        if (id >= n_ || !present_[id]) return 0;
+        if (!dirty_[id]) return score_[id];
+        const uint64_t *nw = row(id);
+        uint64_t s;
+        if (!weighted) {
+            uint64_t inside = 0;   // ordered pairs (a, b) of neighbours that are adjacent
+            for_each(nw, [&](unsigned a) {
+                const uint64_t *na = row(a);
+                for (unsigned w = 0; w < words_; ++w) inside += (uint64_t)__builtin_popcountll(na[w] & nw[w]);
+            });
+            const uint64_t d = deg_[id];
+            s = d * (d - (d ? 1 : 0)) / 2 - inside / 2;
+        } else {
+            uint64_t sum = 0, sq = 0, inside = 0;
+            for_each(nw, [&](unsigned a) {
+                const uint64_t ca = card_.at(a);
+                sum += ca;
+                sq += ca * ca;
+                const uint64_t *na = row(a);
+                uint64_t acc = 0;
+                for (unsigned w = 0; w < words_; ++w) {
+                    uint64_t x = na[w] & nw[w];
+                    while (x) {
+                        const unsigned b = (unsigned)__builtin_ctzll(x);
+                        x &= x - 1;
+                        acc += card_.at(w * 64 + b);
+                    }
+                }
+                inside += ca * acc;
+            });
+            s = (sum * sum - sq) / 2 - inside / 2;
+        }
+        score_[id] = (unsigned)s;   // the reference accumulates in `unsigned`
+        dirty_[id] = 0;
+        return score_[id];
+    }
+
+    unsigned eliminate(unsigned v)
+    {
+        if (v >= n_ || !present_[v]) return 0;
+        std::vector<unsigned> nb;
+        for_each(row(v), [&](unsigned a) { nb.push_back(a); });
+        for (unsigned a : nb) {
+            clear(a, v);
+            --deg_[a];
+            dirty_[a] = 1;
+        }
+        for (size_t i = 0; i < nb.size(); ++i)
+            for (size_t j = i + 1; j < nb.size(); ++j) {
+                const unsigned a = nb[i], b = nb[j];
+                if (test(a, b)) continue;
+                // a new edge changes the fill-in of every common neighbour of its end points
+                const uint64_t *ra = row(a), *rb = row(b);
+                for (unsigned w = 0; w < words_; ++w) {
+                    uint64_t x = ra[w] & rb[w];
+                    while (x) {
+                        const unsigned c = (unsigned)__builtin_ctzll(x);
+                        x &= x - 1;
+                        dirty_[w * 64 + c] = 1;
+                    }
+                }
+                set(a, b);
+                set(b, a);
+                ++deg_[a];
+                ++deg_[b];
+            }
+        std::fill(row(v), row(v) + words_, 0);
+        deg_[v] = 0;
+        present_[v] = 0;
+        --alive_;
+        return (unsigned)nb.size();
+    }
+
+    std::vector<unsigned> card_;
+    unsigned n_ = 0, words_ = 0, alive_ = 0;
+    std::vector<uint64_t> bits_;
+    std::vector<char> present_, dirty_;
+    std::vector<unsigned> deg_, score_;
 };
 
 }  // namespace bnpp

@@ -407,18 +407,35 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
 
 // Graph::ordering on the host (code/graph.cpp:41-195), same tie-breaks as the reference.
 // scopes: factor scopes AFTER conditioning; vars: the variables to order, in the caller's order.
-int bnpp_elim_order(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_vars_to_order,
-                    const uint32_t *vars, int heuristic, uint32_t *order_out, uint32_t *width_out)
+int bnpp_elim_order(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_obs,
+                    const uint32_t *obs_var, int n_vars_to_order, const uint32_t *vars, int heuristic,
+                    uint32_t *order_out, uint32_t *n_order_out, uint32_t *width_out)
 {
-    if (nvars < 0 || nfac < 0 || n_vars_to_order < 0 || heuristic < 0 || heuristic > 2) return BNPP_EINVAL;
+    // heuristic | 0x100 runs the slow path on the reference's own containers (cross-check in tests)
+    const bool reference_containers = (heuristic & 0x100) != 0;
+    heuristic &= 0xff;
+    if (nvars < 0 || nfac < 0 || n_obs < 0 || n_vars_to_order < 0 || heuristic < 0 || heuristic > 2) return BNPP_EINVAL;
+    std::vector<char> observed(nvars > 0 ? nvars : 1, 0);
+    for (int i = 0; i < n_obs; ++i)
+        if (obs_var[i] < (uint32_t)nvars) observed[obs_var[i]] = 1;
+    // the graph of the CONDITIONED factors (code/model.cpp:283-287, 362): observed axes are gone
     std::vector<std::vector<unsigned>> sc(nfac);
-    for (int f = 0; f < nfac; ++f) sc[f].assign(scopes[f].var_id, scopes[f].var_id + scopes[f].rank);
+    for (int f = 0; f < nfac; ++f)
+        for (int i = 0; i < scopes[f].rank; ++i) {
+            const uint32_t v = scopes[f].var_id[i];
+            if (v >= (uint32_t)nvars || !observed[v]) sc[f].push_back(v);
+        }
     std::vector<unsigned> c(card, card + nvars);
     InteractionGraph g(sc, c);
-    std::vector<unsigned> v(vars, vars + n_vars_to_order);
+    std::vector<unsigned> v;
+    for (int i = 0; i < n_vars_to_order; ++i)
+        if (vars[i] >= (uint32_t)nvars || !observed[vars[i]]) v.push_back(vars[i]);
     unsigned width = 0;
-    std::vector<unsigned> order = g.ordering(v, (Heuristic)heuristic, width);
+    std::vector<unsigned> order;
+    if (reference_containers) order = g.ordering(v, (Heuristic)heuristic, width);
+    else order = FastOrderer(g).ordering(v, (Heuristic)heuristic, width);
     for (size_t i = 0; i < order.size(); ++i) order_out[i] = order[i];
+    if (n_order_out) *n_order_out = (uint32_t)order.size();
     if (width_out) *width_out = width;
     return BNPP_OK;
 }

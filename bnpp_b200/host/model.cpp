@@ -112,7 +112,7 @@ Factor Model::eliminate(const std::vector<const Variable*> &variables, const std
         if (options["min-degree"]) h = bnpp::H_MIN_DEGREE;
         else if (options["weighted-min-fill"]) h = bnpp::H_WEIGHTED_MIN_FILL;
         unsigned width = 0;
-        ids = g.ordering(ids, h, width);
+        ids = bnpp::FastOrderer(g).ordering(ids, h, width);
         if (options["verbose"]) {
             // same (mis)label as the reference (code/model.cpp:371-379, SURVEY A.2 iii)
             std::cout << ">> Original elimination order (width = " << g.order_width(ids) << ")" << std::endl << "  ";

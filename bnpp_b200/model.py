@@ -21,7 +21,7 @@ def _declare(L):
         return
     P = ctypes.POINTER
     L.bnpp_elim_order.argtypes = [ctypes.c_int, capi.c_u32p, ctypes.c_int, P(capi.Scope), ctypes.c_int, capi.c_u32p,
-                                  ctypes.c_int, capi.c_u32p, capi.c_u32p]
+                                  ctypes.c_int, capi.c_u32p, ctypes.c_int, capi.c_u32p, capi.c_u32p, capi.c_u32p]
     L.bnpp_order_width.argtypes = [ctypes.c_int, capi.c_u32p, ctypes.c_int, P(capi.Scope), ctypes.c_int, capi.c_u32p,
                                    capi.c_u32p]
     L.bnpp_ve_plan_create.argtypes = [ctypes.c_void_p, ctypes.c_int, P(capi.Scope), ctypes.c_int, capi.c_u32p,
@@ -48,21 +48,26 @@ def _scopes(scope_list, cards):
     return arr, keep
 
 
-def elim_order(cards, scopes, variables, heuristic):
-    """Graph(...).ordering(variables) of code/graph.cpp:41-101 -> (order, width).  Host only."""
+def elim_order(cards, scopes, variables, heuristic, reference_containers=False, observed=(), _arr=None):
+    """Graph(...).ordering(variables) of code/graph.cpp:41-101 -> (order, width).  Host only.
+    `scopes` are ORIGINAL factor scopes; `observed` variables are removed from them (and from
+    `variables`) inside the library, as BN::partition does by conditioning (code/model.cpp:283-287).
+    reference_containers=True runs the slow path on std::unordered_set adjacency (cross-check)."""
     L = capi.lib()
     _declare(L)
-    arr, keep = _scopes(scopes, cards)
+    arr = _arr if _arr is not None else _scopes(scopes, cards)[0]
     c = capi._u32(cards)
     v = capi._u32(variables)
+    ob = capi._u32(list(observed))
     out = (ctypes.c_uint32 * max(1, len(variables)))()
-    width = ctypes.c_uint32()
-    rc = L.bnpp_elim_order(len(cards), ctypes.cast(c, capi.c_u32p), len(scopes), arr, len(variables),
-                           ctypes.cast(v, capi.c_u32p), HEUR[heuristic], ctypes.cast(out, capi.c_u32p),
-                           ctypes.byref(width))
+    width, n = ctypes.c_uint32(), ctypes.c_uint32()
+    rc = L.bnpp_elim_order(len(cards), ctypes.cast(c, capi.c_u32p), len(scopes), arr, len(observed),
+                           ctypes.cast(ob, capi.c_u32p), len(variables), ctypes.cast(v, capi.c_u32p),
+                           HEUR[heuristic] | (0x100 if reference_containers else 0), ctypes.cast(out, capi.c_u32p),
+                           ctypes.byref(n), ctypes.byref(width))
     if rc != 0:
         raise capi.BnppError(rc, "bnpp_elim_order")
-    return list(out[:len(variables)]), width.value
+    return list(out[:n.value]), width.value
 
 
 def order_width(cards, scopes, order):
@@ -82,11 +87,11 @@ def order_width(cards, scopes, order):
 class VEPlan:
     """bnpp_ve_plan: the schedule of fused elimination launches for (scopes, observed ids, order)."""
 
-    def __init__(self, ctx, cards, scopes, observed, order):
+    def __init__(self, ctx, cards, scopes, observed, order, _arr=None):
         self.ctx = ctx
         L = ctx.L
         _declare(L)
-        arr, self._keep = _scopes(scopes, cards)
+        arr, self._keep = (_arr, None) if _arr is not None else _scopes(scopes, cards)
         self.observed = list(observed)
         ov, od = capi._u32(self.observed), capi._u32(order)
         h = ctypes.c_void_p()
@@ -164,6 +169,9 @@ class BN:
             self._dev.copy_(self._host, non_blocking=True)
         self.table_ptrs = [self._dev.data_ptr() + 8 * o for o in offs]
         self._plans = {}
+        self._res2 = None
+        self.last_timing = {}
+        self._scope_arr, self._scope_keep = _scopes(self.scopes, self.cards)   # the model's structure never changes
 
     @property
     def nvars(self):
@@ -180,14 +188,14 @@ class BN:
     def order(self, variables, observed, heuristic=None):
         """the order BN::variable_elimination uses (code/model.cpp:358-369)"""
         if heuristic is None:
-            return list(variables), None
-        return elim_order(self.cards, self.conditioned_scopes(set(observed)), variables, heuristic)
+            return [v for v in variables if v not in observed], None
+        return elim_order(self.cards, self.scopes, variables, heuristic, observed=sorted(observed), _arr=self._scope_arr)
 
     def plan(self, observed, order):
         key = (tuple(observed), tuple(order))
         p = self._plans.get(key)
         if p is None:
-            p = VEPlan(self.ctx, self.cards, self.scopes, observed, order)
+            p = VEPlan(self.ctx, self.cards, self.scopes, observed, order, _arr=self._scope_arr)
             self._plans[key] = p
         return p
 
@@ -206,11 +214,24 @@ class BN:
         evidence = dict(evidence or {})
         variables = [v for v in range(self.nvars) if v not in evidence]
         order, _ = self.order(variables, evidence, heuristic)
-        scope, cards, res = self.variable_elimination(evidence, order)
+        t1 = time.perf_counter()
+        observed = sorted(evidence)
+        p = self.plan(observed, order)
+        t2 = time.perf_counter()
+        if self._res2 is None:
+            with torch.cuda.stream(self.ctx.torch_stream):
+                self._res2 = torch.empty(2, dtype=torch.float64, device=self._dev.device)
+                self._res2_host = torch.empty(2, dtype=torch.float64).pin_memory()
+        assert p.result_size == 1
+        p.run(self.table_ptrs, [evidence[v] for v in observed], self._res2.data_ptr(), self._res2.data_ptr() + 8)
+        with torch.cuda.stream(self.ctx.torch_stream):
+            self._res2_host.copy_(self._res2, non_blocking=True)
         self.ctx.sync()
-        host = res.cpu()
-        assert host.numel() == 2 and host[0].item() == host[1].item()   # code/model.cpp:288
-        return float(host[1].item()), (time.perf_counter() - t0) * 1e3
+        t3 = time.perf_counter()
+        z0, z1 = self._res2_host.tolist()
+        assert z0 == z1      # code/model.cpp:288
+        self.last_timing = {"order_ms": (t1 - t0) * 1e3, "plan_ms": (t2 - t1) * 1e3, "run_ms": (t3 - t2) * 1e3}
+        return z1, (time.perf_counter() - t0) * 1e3
 
     def marginals(self, evidence=None, heuristic=None):
         """BN::marginals, VE branch (code/model.cpp:320-339): one VE pass per variable, normalised.

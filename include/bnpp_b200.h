@@ -131,11 +131,17 @@ int bnpp_reduce(bnpp_ctx *ctx, int op, uint64_t n, const double *in_dev, double 
 /* ---- device-resident variable elimination -------------------------------------- */
 /* Graph::ordering / min_fill / weighted_min_fill / min_degree (code/graph.cpp:41-195) on
  * the HOST with the reference's tie-breaks (libstdc++ unordered_set iteration order).
- * scopes: the factor scopes the graph is built from (already conditioned);
- * vars: the variables to order, in the caller's order; heuristic: 0 = min-fill,
- * 1 = weighted min-fill, 2 = min-degree.  Needs no device. */
-int bnpp_elim_order(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_vars_to_order,
-                    const uint32_t *vars, int heuristic, uint32_t *order_out, uint32_t *width_out);
+ *   scopes  : ORIGINAL factor scopes; obs_var[n_obs] are removed from them first, which
+ *             is the graph BN::partition builds from its conditioned factors
+ *             (code/model.cpp:283-287, 362);
+ *   vars    : the variables to order, in the caller's order (observed ones are dropped:
+ *             the reference crashes on them, SURVEY A.2 i);
+ *   heuristic: 0 = min-fill, 1 = weighted min-fill, 2 = min-degree; | 0x100 selects the
+ *             slow implementation on the reference's own containers (cross-check).
+ * order_out must hold n_vars_to_order ids; *n_order_out receives the count.  Needs no device. */
+int bnpp_elim_order(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_obs,
+                    const uint32_t *obs_var, int n_vars_to_order, const uint32_t *vars, int heuristic,
+                    uint32_t *order_out, uint32_t *n_order_out, uint32_t *width_out);
 /* Graph::order_width, code/graph.cpp:197-237 (host). */
 int bnpp_order_width(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_order,
                      const uint32_t *order, uint32_t *width_out);

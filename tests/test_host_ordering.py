@@ -78,3 +78,18 @@ def test_orders_models_and_synthetic(golden_models, golden_synth):
         for case in rec["cases"]:
             order, width = model.elim_order(cards, cond, variables, case["flag"])
             assert order == case["order"] and width == case["width"]
+
+
+def test_fast_orderer_equals_reference_containers(golden_orders):
+    """the bit-matrix orderer and the std::unordered_set one (the reference's containers) agree on
+    every shipped network, every heuristic, with and without observed variables handled in-library"""
+    for name, rec in golden_orders.items():
+        if len(rec["card"]) > 450:
+            continue        # the container path is quadratic; the big nets are pinned by test_orders_bit_exact
+        cards, scopes = rec["card"], rec["scopes"]
+        for case in rec["cases"]:
+            obs = case["observed"]
+            allv = list(range(len(cards)))
+            fast = model.elim_order(cards, scopes, allv, case["flag"], observed=obs)
+            slow = model.elim_order(cards, scopes, allv, case["flag"], reference_containers=True, observed=obs)
+            assert fast == slow == (case["order"], case["width"]), (name, case["flag"])
