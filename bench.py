@@ -215,10 +215,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
-        one_query_device(plan, obs_val, res)
-        st = plan.step_stats()          # synchronises on the last launch of this query
-        per_launch = st if per_launch is None else [
-            dict(a, ms=a["ms"] + b["ms"]) for a, b in zip(per_launch, st)]
+        one_query_device(plan, obs_val, res)     # per-launch CUDA events are recorded on the stream, no host sync
     if world > 1:
         with torch.cuda.stream(stream):
             zall = res[1:].clone()
@@ -229,6 +226,7 @@ def main():
         dist.barrier()
     dev_ms = e0.elapsed_time(e1)
     gpu_launches = ctx.launches - launches0
+    per_launch = plan.step_stats()       # events of the LAST timed query (each launch bracketed on the launching stream)
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -278,12 +276,12 @@ def main():
     peak, peak_kind = peaks()
     widest = max(range(len(per_launch)), key=lambda i: per_launch[i]["bytes"])
     wl = per_launch[widest]
-    w_ms = wl["ms"] / args.steps
+    w_ms = wl["ms"]
     achieved = wl["bytes"] / w_ms / 1e6
     big = [s for s in per_launch if s["entries"] >= (1 << 24)]
     big_bytes = sum(s["bytes"] for s in big)
-    big_ms = sum(s["ms"] for s in big) / args.steps
-    all_ms = sum(s["ms"] for s in per_launch) / args.steps
+    big_ms = sum(s["ms"] for s in big)
+    all_ms = sum(s["ms"] for s in per_launch)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_kind": peak_kind,
                 "kernel": "contract_fast (fused product+sum-out), widest launch: k=%d operands, %d union entries, "
