@@ -20,6 +20,7 @@
 #include <map>
 #include <vector>
 
+#include "batched.hpp"
 #include "common.cuh"
 #include "elim_order.hpp"
 
@@ -402,6 +403,69 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
     if (pl->profiling) cudaEventRecord(pl->ev[pl->steps.size()], ctx->stream);
     for (double *p : owned)
         if (p) bnpp_free(ctx, p);
+    return rc;
+}
+
+// BN::partition for a whole batch of evidence sets over ONE plan (config 5): the observed
+// ids are the plan's, ev_dev[b][j] is the value of obs_var[j] in set b.  result_dev receives
+// [result_size][nb] (batch fastest).  Sets are processed in slices that keep the widest
+// intermediate below ~1 GiB.
+int bnpp_ve_plan_run_batched(bnpp_ve_plan *pl, const double *const *tables_dev, uint32_t nb, uint32_t n_obs,
+                             const uint8_t *ev_dev, double *result_dev)
+{
+    if (!pl || !result_dev || nb == 0) return BNPP_EINVAL;
+    bnpp_ctx *ctx = pl->ctx;
+    uint64_t widest = 1;
+    for (const PlanFactor &pf : pl->f)
+        if (pf.src < 0) widest = std::max(widest, pf.size);
+    widest = std::max(widest, pl->result_size);
+    uint32_t slice = (uint32_t)std::min<uint64_t>(nb, std::max<uint64_t>(1, (1ull << 27) / widest));
+    if (pl->result_size > 1) slice = nb;     // a multi-entry result is laid out [entries][nb]: no slicing
+    if ((uint64_t)widest * slice >= (1ull << 32)) return fail(ctx, BNPP_ETOOBIG, "batched VE: intermediate too large");
+    static const std::vector<int64_t> dense;
+    static const std::vector<std::pair<int64_t, int>> no_obs;
+    int rc = BNPP_OK;
+    for (uint32_t b0 = 0; b0 < nb && rc == BNPP_OK; b0 += slice) {
+        const uint32_t cur = std::min(slice, nb - b0);
+        std::vector<double *> owned(pl->f.size(), nullptr);
+        for (size_t s = 0; s < pl->steps.size() && rc == BNPP_OK; ++s) {
+            const PlanStep &st = pl->steps[s];
+            BatchedOperandDesc ops[kMaxK];
+            for (size_t q = 0; q < st.operands.size(); ++q) {
+                const PlanFactor &pf = pl->f[st.operands[q]];
+                ops[q].batched = pf.src < 0;
+                ops[q].ptr = pf.src < 0 ? owned[st.operands[q]] : tables_dev[pf.src];
+                ops[q].var = &pf.var;
+                ops[q].card = &pf.card;
+                ops[q].stride = pf.src < 0 ? &dense : &pf.stride;
+                ops[q].obs = pf.src < 0 ? &no_obs : &pf.obs;
+            }
+            double *dst;
+            const std::vector<uint32_t> *ov, *oc;
+            if (st.out == -2) {
+                ov = &pl->result_var;
+                oc = &pl->result_card;
+                dst = result_dev + b0;   // result_size == 1 when slicing
+            } else {
+                const PlanFactor &of = pl->f[st.out];
+                ov = &of.var;
+                oc = &of.card;
+                rc = bnpp_alloc(ctx, of.size * cur, &owned[st.out]);
+                if (rc != BNPP_OK) break;
+                dst = owned[st.out];
+            }
+            rc = contract_batched_step(ctx, (int)st.operands.size(), ops, *ov, *oc, st.elim, cur,
+                                       ev_dev + (uint64_t)b0 * n_obs, n_obs, dst);
+            for (int id : st.operands)
+                if (owned[id] && pl->f[id].last_use == (int)s) {
+                    bnpp_free(ctx, owned[id]);
+                    owned[id] = nullptr;
+                }
+        }
+        for (double *p : owned)
+            if (p) bnpp_free(ctx, p);
+        if (pl->steps.empty() || pl->steps.back().out != -2) rc = fill(ctx, result_dev + b0, cur, 1.0);
+    }
     return rc;
 }
 

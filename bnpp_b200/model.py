@@ -30,6 +30,8 @@ def _declare(L):
     L.bnpp_ve_plan_info.argtypes = [ctypes.c_void_p, P(ctypes.c_int32), capi.c_u32p, capi.c_u32p, capi.c_u64p,
                                     capi.c_u64p, capi.c_u64p, capi.c_u64p, capi.c_u64p]
     L.bnpp_ve_plan_run.argtypes = [ctypes.c_void_p, P(ctypes.c_void_p), capi.c_u32p, ctypes.c_void_p, ctypes.c_void_p]
+    L.bnpp_ve_plan_run_batched.argtypes = [ctypes.c_void_p, P(ctypes.c_void_p), ctypes.c_uint32, ctypes.c_uint32,
+                                           ctypes.c_void_p, ctypes.c_void_p]
     L.bnpp_ve_plan_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.bnpp_ve_plan_step_stats.argtypes = [ctypes.c_void_p, ctypes.c_uint64, P(ctypes.c_float), capi.c_u64p, capi.c_u64p,
                                           P(ctypes.c_int32)]
@@ -115,6 +117,13 @@ class VEPlan:
         ov = capi._u32(obs_val)
         self.ctx.check(self.ctx.L.bnpp_ve_plan_run(self.h, tp, ctypes.cast(ov, capi.c_u32p), ctypes.c_void_p(result_ptr),
                                                    ctypes.c_void_p(z_ptr) if z_ptr else None))
+
+    def run_batched(self, table_ptrs, nb, ev_ptr, result_ptr):
+        """ev_ptr: device uint8 [nb][len(observed)]; result_ptr: device double [result_size][nb]"""
+        n = len(table_ptrs)
+        tp = (ctypes.c_void_p * max(1, n))(*table_ptrs)
+        self.ctx.check(self.ctx.L.bnpp_ve_plan_run_batched(self.h, tp, int(nb), len(self.observed),
+                                                           ctypes.c_void_p(ev_ptr), ctypes.c_void_p(result_ptr)))
 
     def set_profiling(self, on=True):
         self.ctx.check(self.ctx.L.bnpp_ve_plan_set_profiling(self.h, int(on)))
@@ -232,6 +241,24 @@ class BN:
         assert z0 == z1      # code/model.cpp:288
         self.last_timing = {"order_ms": (t1 - t0) * 1e3, "plan_ms": (t2 - t1) * 1e3, "run_ms": (t3 - t2) * 1e3}
         return z1, (time.perf_counter() - t0) * 1e3
+
+    def partition_batch(self, observed, values, heuristic="mf", host_values=None):
+        """PR for a batch of evidence sets sharing the observed ids (config 5).
+        observed: sorted variable ids; values: torch.uint8 CUDA tensor [nb][len(observed)] (or pass
+        host_values, a pinned uint8 tensor, to include the H2D copy).  -> device tensor [nb] of Z."""
+        observed = list(observed)
+        variables = [v for v in range(self.nvars) if v not in set(observed)]
+        order, _ = self.order(variables, observed, heuristic)
+        p = self.plan(observed, order)
+        assert p.result_size == 1
+        with torch.cuda.stream(self.ctx.torch_stream):
+            if host_values is not None:
+                values = host_values.to(self._dev.device, non_blocking=True)
+            nb = values.shape[0]
+            out = torch.empty(nb, dtype=torch.float64, device=self._dev.device)
+        p.run_batched(self.table_ptrs, nb, values.data_ptr(), out.data_ptr())
+        self._keep_alive = values
+        return out
 
     def marginals(self, evidence=None, heuristic=None):
         """BN::marginals, VE branch (code/model.cpp:320-339): one VE pass per variable, normalised.

