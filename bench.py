@@ -37,7 +37,9 @@ METRIC = "factor entries/sec (fused product+sum-out), VE PR on 2^28-entry tables
 UNIT = "entries/s"
 
 # config 4 per GPU count: (N, W, K, seed) of bnpp_b200.synth.random_bn_uai and the min-fill width
-WIDE = {1: (64, 40, 4, 5), 2: (64, 40, 4, 3), 4: (64, 40, 4, 6), 8: (64, 40, 4, 8)}
+# (chosen with the host orderer so that fixing log2(N) shard variables leaves every rank a width-27 problem
+# of ~2.2e9 union entries: 1 GPU 2.217e9, 2 GPUs 2.190e9, 4 GPUs 2.153e9, 8 GPUs 2.031e9 per rank)
+WIDE = {1: (64, 40, 4, 5), 2: (68, 40, 4, 27), 4: (72, 40, 4, 23), 8: (76, 44, 4, 3)}
 # bounded CPU sample: same generator, narrower (the reference needs ~1 us per entry)
 CPU_SAMPLE = (48, 26, 4, 3)
 
@@ -282,8 +284,13 @@ def main():
     big_bytes = sum(s["bytes"] for s in big)
     big_ms = sum(s["ms"] for s in big)
     all_ms = sum(s["ms"] for s in per_launch)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if n_gpus == 1 and os.path.exists(tp):
+        tj = json.load(open(tp))      # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_kind": peak_kind,
+                "traffic": traffic, "algorithmic_bytes": wl["bytes"], "peak_kind": peak_kind,
                 "kernel": "contract_fast (fused product+sum-out), widest launch: k=%d operands, %d union entries, "
                           "%.3f GB algorithmic, %.3f ms" % (wl["k"], wl["entries"], wl["bytes"] / 1e9, w_ms),
                 "launches_ge_2p24_entries": {"n": len(big), "GBs": big_bytes / big_ms / 1e6 if big_ms else None,
