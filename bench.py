@@ -169,7 +169,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from bnpp_b200 import capi, model, synth
+    from bnpp_b200 import capi, model, sharding, synth
 
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -189,8 +189,8 @@ def main():
     shard_vars, evidence = [], {}
     if n_gpus > 1:
         g = n_gpus.bit_length() - 1
-        shard_vars = pick_shard_vars(bn.scopes, full_order, g)
-        evidence = {v: (rank >> i) & 1 for i, v in enumerate(shard_vars)}
+        shard_vars = sharding.pick_shard_vars(bn.scopes, full_order, g)
+        evidence = sharding.shard_evidence(shard_vars, rank)
     variables = [v for v in range(N) if v not in evidence]
 
     def one_query_device(plan, obs_val, res):
@@ -319,25 +319,6 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
-
-
-def pick_shard_vars(scopes, order, g):
-    """the g variables of the widest elimination clique that the order eliminates last"""
-    rank = {v: i for i, v in enumerate(order)}
-    buckets = {v: [] for v in order}
-    for sc in scopes:
-        buckets[min(sc, key=rank.get)].append(set(sc))
-    best, best_u = -1, None
-    for v in order:
-        if not buckets[v]:
-            continue
-        u = set().union(*buckets[v])
-        if len(u) > best:
-            best, best_u = len(u), set(u)
-        u.discard(v)
-        if u:
-            buckets[min(u, key=rank.get)].append(u)
-    return sorted(best_u, key=rank.get)[-g:]
 
 
 if __name__ == "__main__":

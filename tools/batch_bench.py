@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from bnpp_b200 import capi, model, synth  # noqa: E402
+from bnpp_b200 import capi, model, sharding, synth  # noqa: E402
 
 
 def main():
@@ -36,7 +36,7 @@ def main():
     _, bn = model.from_uai_text(ctx, synth.random_bn_uai(N, W, K, seed))
     evs = synth.evidence_batch(N, nobs, args.sets, seed=5, fixed_ids=True)
     observed = sorted(evs[0])
-    lo, hi = rank * args.sets // world, (rank + 1) * args.sets // world      # contiguous shard, no communication
+    lo, hi = sharding.batch_slice(rank, world, args.sets)      # contiguous shard, no communication
     host = torch.tensor([[ev[v] for v in observed] for ev in evs[lo:hi]], dtype=torch.uint8).pin_memory()
     dev = host.cuda()
     s = ctx.torch_stream
