@@ -245,7 +245,7 @@ def main():
 
     # ---- e2e: through the public API from host buffers -----------------------------------------
     for _ in range(2):
-        bn._plans.clear()
+        bn.drop_plans()
         bn.reupload()
         bn.partition(evidence, "mf")
     if world > 1:
@@ -254,7 +254,7 @@ def main():
     t0 = time.perf_counter()
     e2e_parts = {}
     for _ in range(args.steps):
-        bn._plans.clear()               # nothing cached: ordering + planning are paid every step
+        bn.drop_plans()               # nothing cached: ordering + planning are paid every step
         bn.reupload()                   # pinned host CPTs -> HBM
         z_e2e, _ = bn.partition(evidence, "mf")     # ... launches ... scalar -> host
         for kk, vv in bn.last_timing.items():

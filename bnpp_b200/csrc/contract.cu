@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "contract.hpp"
 
 namespace bnpp {
 
@@ -48,44 +49,6 @@ enum LoadClass : uint8_t {
     LC_S_X,         // two 8-byte loads along x                                               -> r[x]
     LC_S_L,         // two 8-byte loads along the innermost output axis                       -> r[j]
     LC_S_JX,        // four 8-byte loads                                                      -> r[2j+x]
-};
-
-struct ParamsHead {
-    const double *in[kMaxK];
-    double *out;
-    double *partials;
-    unsigned int *ticket;
-    double *z;
-    unsigned int *status;
-    uint64_t n_items;           // output entries / V
-    uint32_t cx;                // cardinality of the eliminated variable (1 = none)
-    uint32_t sx[kMaxK];         // operand stride of the eliminated variable
-    uint32_t sl[kMaxK];         // operand stride between the V entries of an item
-    uint32_t sol;               // output stride between the V entries of an item
-    uint8_t cls[kMaxK];
-    uint8_t out_vec;            // 16-byte store allowed
-};
-
-// Mixed-radix iteration space: digits by multiply-high division, outermost axis first.
-struct ParamsMR {
-    ParamsHead h;
-    uint32_t R;
-    FastDiv div[kMaxR];
-    uint32_t so[kMaxR];         // output stride per axis (per item on the innermost axis)
-    uint32_t s[kMaxK][kMaxR];   // operand stride per axis
-};
-
-// Power-of-two iteration space: off = sum_f ((item >> sh) & mask) * mul, fields merged PER
-// OPERAND, so an operand laid out like the output costs one field no matter how
-// scattered the other operands' axes are.
-constexpr int kMaxF = 24;
-struct Field {
-    uint32_t mask, mul, sh;
-};
-struct ParamsP2 {
-    ParamsHead h;
-    uint8_t nf[kMaxK + 1];      // [K] is the output
-    Field f[kMaxK + 1][kMaxF];
 };
 
 template <int K>
@@ -239,7 +202,7 @@ __global__ void __launch_bounds__(kBlock) contract_fast(const __grid_constant__ 
         }
     }
     if (DIV && zero_div) atomicOr(h.status, BNPP_STATUS_ZERO_DIVISOR);
-    grid_sum_to(zacc, h.partials, h.ticket, h.z);
+    if (h.z) grid_sum_to(zacc, h.partials, h.ticket, h.z);   // grid-uniform: intermediates of a VE plan need no partition
 }
 
 // Power-of-two iteration space, the hot variant.  A CTA owns chunks of CH = U * kBlock
@@ -300,7 +263,7 @@ __global__ void __launch_bounds__(kBlock) contract_fast_p2s(const __grid_constan
         }
     }
     if (DIV && zero_div) atomicOr(h.status, BNPP_STATUS_ZERO_DIVISOR);
-    grid_sum_to(zacc, h.partials, h.ticket, h.z);
+    if (h.z) grid_sum_to(zacc, h.partials, h.ticket, h.z);   // grid-uniform: intermediates of a VE plan need no partition
 }
 
 // The variable-elimination hot variant.  With the canonical axis order of ve.cu every
@@ -355,7 +318,7 @@ __global__ void __launch_bounds__(kBlock) contract_canon(const __grid_constant__
             *reinterpret_cast<double2 *>(h.out + (ohi + olo[u])) = make_double2(r0, r1);
         }
     }
-    grid_sum_to(zacc, h.partials, h.ticket, h.z);
+    if (h.z) grid_sum_to(zacc, h.partials, h.ticket, h.z);   // grid-uniform: intermediates of a VE plan need no partition
 }
 
 // Generic path: any cardinality of the eliminated variable, one output entry per item.
@@ -384,7 +347,7 @@ __global__ void __launch_bounds__(kBlock) contract_generic(const __grid_constant
         zacc = __dadd_rn(zacc, acc);
     }
     if (DIV && zero_div) atomicOr(h.status, BNPP_STATUS_ZERO_DIVISOR);
-    grid_sum_to(zacc, h.partials, h.ticket, h.z);
+    if (h.z) grid_sum_to(zacc, h.partials, h.ticket, h.z);   // grid-uniform: intermediates of a VE plan need no partition
 }
 
 // ---------------------------------------------------------------------------
@@ -537,8 +500,22 @@ static void note_launch(bnpp_ctx *ctx, const ParamsHead &h, const char *variant,
     ctx->last_block = kBlock;
 }
 
+static void describe(LaunchDesc *d, const ParamsHead &h, const void *fn, uint64_t blocks, const char *variant, int k, int C,
+                     int V, int U, bool div, bool generic, uint32_t R)
+{
+    d->fn = fn;
+    d->grid = (unsigned)blocks;
+    d->k = k;
+    char nm[128];
+    if (generic) snprintf(nm, sizeof nm, "contract_generic<%s,K=%d,div=%d> cx=%u R=%u", variant, k, div, h.cx, R);
+    else snprintf(nm, sizeof nm, "contract_fast<%s,K=%d,C=%d,V=%d,U=%d,div=%d> R=%u cls=%d,%d,%d", variant, k, C, V, U, div, R,
+                  h.cls[0], k > 1 ? h.cls[1] : -1, k > 2 ? h.cls[2] : -1);
+    d->name = nm;
+}
+
 template <class P>
-static int launch(bnpp_ctx *ctx, P &p, int k, int C, int V, bool div, bool generic, const char *mode, uint32_t R)
+static int plan_launch(bnpp_ctx *ctx, LaunchDesc *d, const P &p, int k, int C, int V, bool div, bool generic, const char *mode,
+                       uint32_t R)
 {
     int U = 1;
     typename Launch<P>::fn_t fn = Launch<P>::pick(k, C, V, div, generic, U);
@@ -546,13 +523,11 @@ static int launch(bnpp_ctx *ctx, P &p, int k, int C, int V, bool div, bool gener
     const uint64_t cap = resident_ctas(ctx, fn);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    fn<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(p);
-    BNPP_CUDA(ctx, cudaGetLastError());
-    note_launch(ctx, p.h, mode, k, C, V, U, div, generic, R, blocks);
+    describe(d, p.h, reinterpret_cast<const void *>(fn), blocks, mode, k, C, V, U, div, generic, R);
     return BNPP_OK;
 }
 
-static int launch_p2s(bnpp_ctx *ctx, ParamsP2 &p, int k, int C, int V, bool div, uint32_t R, bool &done)
+static bool plan_launch_p2s(bnpp_ctx *ctx, LaunchDesc *d, const ParamsP2 &p, int k, int C, int V, bool div, uint32_t R)
 {
     int U = 1;
     p2s_fn fn = nullptr;
@@ -582,22 +557,45 @@ static int launch_p2s(bnpp_ctx *ctx, ParamsP2 &p, int k, int C, int V, bool div,
     }
     if (!fn) fn = pick_p2s(k, C, V, div, U);
     const uint64_t ch = (uint64_t)kBlock * U;
-    done = false;
-    if (p.h.n_items < ch || p.h.n_items % ch) return BNPP_OK;   // tiny problem: per-item kernel
+    if (p.h.n_items < ch || p.h.n_items % ch) return false;   // tiny problem: per-item kernel
     uint64_t blocks = p.h.n_items / ch;
     const uint64_t cap = resident_ctas(ctx, fn);
     if (blocks > cap) blocks = cap;
-    fn<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(p);
-    BNPP_CUDA(ctx, cudaGetLastError());
-    note_launch(ctx, p.h, variant, k, C, V, U, div, false, R, blocks);
-    done = true;
+    describe(d, p.h, reinterpret_cast<const void *>(fn), blocks, variant, k, C, V, U, div, false, R);
+    return true;
+}
+
+int contract_launch(bnpp_ctx *ctx, LaunchDesc &d, const double *const *in, double *out, double *z)
+{
+    ParamsHead &h = d.head();
+    for (int q = 0; q < d.k; ++q) h.in[q] = in[q];
+    h.out = out;
+    h.z = z;
+    void *args[1];
+    args[0] = d.p2 ? static_cast<void *>(&d.p2p) : static_cast<void *>(&d.mrp);
+    BNPP_CUDA(ctx, cudaLaunchKernel(d.fn, dim3(d.grid), dim3(kBlock), args, 0, ctx->stream));
+    ctx->launches++;
+    ctx->last_kernel = d.name;
+    ctx->last_grid = d.grid;
+    ctx->last_block = kBlock;
     return BNPP_OK;
 }
 
-int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope,
-             int64_t elim_var, int divide, double *out_dev, double *z_dev)
+int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope, int64_t elim_var, int divide,
+             double *out_dev, double *z_dev)
 {
-    if (!ctx) return BNPP_EINVAL;
+    LaunchDesc d;
+    const int rc = contract_plan(ctx, k, ops, out_scope, elim_var, divide, out_dev, z_dev, &d);
+    if (rc != BNPP_OK) return rc;
+    const double *in[kMaxK];
+    for (int q = 0; q < k; ++q) in[q] = ops[q].data;
+    return contract_launch(ctx, d, in, out_dev, z_dev);
+}
+
+int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope, int64_t elim_var,
+                  int divide, double *out_dev, double *z_dev, LaunchDesc *desc)
+{
+    if (!ctx || !desc) return BNPP_EINVAL;
     if (k < 1 || k > kMaxK) return fail(ctx, BNPP_ERANK, "product_sum_out: operand count must be 1..BNPP_MAX_OPERANDS");
     if (divide && k != 2) return fail(ctx, BNPP_EINVAL, "divide needs exactly two operands");
     if (!out_scope || out_scope->rank < 0 || out_scope->rank > BNPP_MAX_RANK)
@@ -786,14 +784,14 @@ int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *ou
 
     h.partials = ctx->partials;
     h.ticket = ctx->ticket;
-    h.z = z_dev ? z_dev : ctx->scratch_z;
+    h.z = z_dev;
     h.status = ctx->status;
 
     // ---- power-of-two iteration space: per-operand bit-fields --------------------
     bool p2 = true;
     for (uint32_t a = 0; a < R; ++a) p2 = p2 && is_pow2(m[a].ext);
     if (p2) {
-        ParamsP2 p;
+        ParamsP2 &p = desc->p2p;
         memset(&p, 0, sizeof p);
         p.h = h;
         bool fits = true;
@@ -825,16 +823,15 @@ int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *ou
             }
             p.nf[q] = (uint8_t)nf;
         }
-        if (fits && !generic) {
-            bool done = false;
-            const int rc = launch_p2s(ctx, p, k, C, V, divide != 0, R, done);
-            if (rc != BNPP_OK || done) return rc;
+        if (fits) {
+            desc->p2 = true;
+            if (!generic && plan_launch_p2s(ctx, desc, p, k, C, V, divide != 0, R)) return BNPP_OK;
+            return plan_launch(ctx, desc, p, k, C, V, divide != 0, generic, "p2", R);
         }
-        if (fits) return launch(ctx, p, k, C, V, divide != 0, generic, "p2", R);
     }
 
     if ((int)R > kMaxR) return fail(ctx, BNPP_ERANK, "more than BNPP_MAX_AXES non-mergeable axes");
-    ParamsMR p;
+    ParamsMR &p = desc->mrp;
     memset(&p, 0, sizeof p);
     p.h = h;
     p.R = R;
@@ -843,7 +840,8 @@ int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *ou
         p.so[a] = (uint32_t)m[a].so;
         for (int q = 0; q < k; ++q) p.s[q][a] = (uint32_t)m[a].s[q];
     }
-    return launch(ctx, p, k, C, V, divide != 0, generic, "mr", R);
+    desc->p2 = false;
+    return plan_launch(ctx, desc, p, k, C, V, divide != 0, generic, "mr", R);
 }
 
 }  // namespace bnpp

@@ -22,6 +22,7 @@
 
 #include "batched.hpp"
 #include "common.cuh"
+#include "contract.hpp"
 #include "elim_order.hpp"
 
 namespace bnpp {
@@ -54,6 +55,13 @@ struct bnpp_ve_plan {
     std::vector<uint32_t> result_var, result_card;
     uint64_t result_size = 1;
     uint64_t union_entries = 0, bytes = 0, peak_bytes = 0, max_step_entries = 0;
+    // replay state: one resolved launch per step and a fixed arena for the intermediates, so a
+    // run is pointer patching + cudaLaunchKernel (the host must not be what small steps wait for)
+    std::vector<bnpp::LaunchDesc> exec;
+    std::vector<uint64_t> arena_off;        // per PlanFactor, in doubles
+    uint64_t arena_doubles = 0;
+    double *arena = nullptr;
+    bool exec_ok = false;
     bool profiling = false;
     std::vector<cudaEvent_t> ev;
     std::vector<float> step_ms;
@@ -132,31 +140,39 @@ uint64_t union_size(const bnpp_ve_plan *pl, const std::vector<int> &ops)
 constexpr uint64_t kWideEntries = 1ull << 20;
 void fold_small(bnpp_ve_plan *pl, std::vector<int> &ops, const std::map<uint32_t, uint64_t> &rank)
 {
-    if (ops.size() < 2) return;
-    std::stable_sort(ops.begin(), ops.end(), [pl](int a, int b) { return pl->f[a].size < pl->f[b].size; });
-    const uint64_t big = pl->f[ops.back()].size;
-    if (big < kWideEntries) return;
-    const uint64_t cap = std::max<uint64_t>(1ull << 12, big >> 4);
-    // longest prefix (smallest operands) whose joint table stays small
-    size_t m = 0;
-    while (m < ops.size() - 1) {
-        std::vector<int> head(ops.begin(), ops.begin() + m + 1);
-        if (pl->f[ops[m]].size > cap || union_size(pl, head) > cap) break;
-        ++m;
-    }
-    // a lone small operand is folded (= copied into canonical axis order) only when it is a
-    // raw input view, whose file-order layout would otherwise force scalar gathers
-    if (m == 0 || (m == 1 && pl->f[ops[0]].src < 0)) return;
-    std::vector<int> work(ops.begin(), ops.begin() + m);
-    while ((int)work.size() > kMaxK) {
-        std::vector<int> part(work.begin(), work.begin() + kMaxK);
+    if (ops.empty()) return;
+    const uint64_t whole = union_size(pl, ops);          // entries the bucket's launch iterates over
+    if (whole < kWideEntries) return;
+    const uint64_t cap = std::max<uint64_t>(1ull << 12, whole >> 5);
+    auto merge = [&](std::vector<int> part) {
         const int t = add_step(pl, part, -1, rank, false);
-        work.erase(work.begin(), work.begin() + kMaxK);
-        work.insert(work.begin(), t);
+        return t;
+    };
+    // repeatedly multiply together the two smallest operands while their joint table stays small
+    for (;;) {
+        std::stable_sort(ops.begin(), ops.end(), [pl](int a, int b) { return pl->f[a].size < pl->f[b].size; });
+        if (ops.size() < 2) break;
+        // the smallest operand and the partner giving the smallest joint table
+        size_t best = 0;
+        uint64_t best_size = UINT64_MAX;
+        for (size_t j = 1; j < ops.size(); ++j) {
+            const uint64_t u = union_size(pl, {ops[0], ops[j]});
+            if (u < best_size) { best_size = u; best = j; }
+        }
+        if (best == 0 || best_size > cap || (ops.size() == 2 && pl->f[ops[1]].size > cap)) break;
+        if (ops.size() == 2) {
+            // two small tables left: one launch over `whole` entries either way, nothing to gain
+            break;
+        }
+        const int a = ops[0], b = ops[best];
+        ops.erase(ops.begin() + best);
+        ops.erase(ops.begin());
+        ops.push_back(merge({a, b}));
     }
-    const int t = add_step(pl, work, -1, rank, false);
-    ops.erase(ops.begin(), ops.begin() + m);
-    ops.insert(ops.begin(), t);
+    // a raw input view keeps its file-order layout, which forces scalar gathers in a wide launch:
+    // copy it once into canonical axis order (K = 1 product)
+    for (int &id : ops)
+        if (pl->f[id].src >= 0 && pl->f[id].size <= cap) id = merge({id});
 }
 
 // the kernel takes at most BNPP_MAX_OPERANDS tables: fold the smallest ones first
@@ -170,6 +186,94 @@ void shrink(bnpp_ve_plan *pl, std::vector<int> &ops, const std::map<uint32_t, ui
         const int t = add_step(pl, head, -1, rank, false);
         ops.erase(ops.begin(), ops.begin() + m);
         ops.insert(ops.begin(), t);
+    }
+}
+
+// Arena layout (first-fit over the step sequence, 256-byte granules) and one resolved launch per
+// step.  Descriptors are planned against stand-in pointers that carry only the ALIGNMENT the
+// real ones are guaranteed to have: intermediates sit on 256-byte boundaries of the arena;
+// an input view is its table (required 32-byte aligned at run time, else the dynamic path
+// is taken) plus a base offset that is a multiple of gcd(strides of its observed axes).
+void build_exec(bnpp_ve_plan *pl)
+{
+    const uint64_t gran = 32;   // doubles
+    pl->arena_off.assign(pl->f.size(), 0);
+    std::vector<std::pair<uint64_t, uint64_t>> free_list;   // (offset, size)
+    uint64_t top = 0;
+    auto take = [&](uint64_t n) {
+        n = (n + gran - 1) / gran * gran;
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].second >= n) {
+                const uint64_t off = free_list[i].first;
+                free_list[i].first += n;
+                free_list[i].second -= n;
+                if (!free_list[i].second) free_list.erase(free_list.begin() + i);
+                return off;
+            }
+        const uint64_t off = top;
+        top += n;
+        return off;
+    };
+    auto give = [&](uint64_t off, uint64_t n) {
+        n = (n + gran - 1) / gran * gran;
+        free_list.push_back({off, n});
+        std::sort(free_list.begin(), free_list.end());
+        for (size_t i = 0; i + 1 < free_list.size();)
+            if (free_list[i].first + free_list[i].second == free_list[i + 1].first) {
+                free_list[i].second += free_list[i + 1].second;
+                free_list.erase(free_list.begin() + i + 1);
+            } else ++i;
+        if (!free_list.empty() && free_list.back().first + free_list.back().second == top) {
+            top = free_list.back().first;
+            free_list.pop_back();
+        }
+    };
+    for (size_t s = 0; s < pl->steps.size(); ++s) {
+        const PlanStep &st = pl->steps[s];
+        if (st.out >= 0) pl->arena_off[st.out] = take(pl->f[st.out].size);
+        pl->arena_doubles = std::max(pl->arena_doubles, top);
+        for (int id : st.operands)
+            if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) give(pl->arena_off[id], pl->f[id].size);
+    }
+
+    double *const arena_standin = reinterpret_cast<double *>(uintptr_t(1) << 32);
+    double *const table_standin = reinterpret_cast<double *>(uintptr_t(2) << 32);
+    double *const result_standin = reinterpret_cast<double *>((uintptr_t(3) << 32) + 8);   // only 8-byte alignment assumed
+    pl->exec.assign(pl->steps.size(), LaunchDesc());
+    pl->exec_ok = true;
+    for (size_t s = 0; s < pl->steps.size() && pl->exec_ok; ++s) {
+        const PlanStep &st = pl->steps[s];
+        bnpp_operand ops[kMaxK];
+        for (size_t q = 0; q < st.operands.size(); ++q) {
+            const PlanFactor &pf = pl->f[st.operands[q]];
+            if (pf.src < 0) {
+                ops[q].data = arena_standin + pl->arena_off[st.operands[q]];
+            } else {
+                uint64_t g = 4;
+                for (auto &o : pf.obs) g = std::__gcd<uint64_t>(g, (uint64_t)o.first);
+                ops[q].data = table_standin + (g >= 4 ? 0 : g);
+            }
+            ops[q].scope.rank = (int32_t)pf.var.size();
+            ops[q].scope.var_id = pf.var.data();
+            ops[q].scope.card = pf.card.data();
+            ops[q].stride = pf.stride.empty() ? nullptr : pf.stride.data();
+        }
+        bnpp_scope os;
+        double *dst;
+        if (st.out == -2) {
+            os.rank = (int32_t)pl->result_var.size();
+            os.var_id = pl->result_var.data();
+            os.card = pl->result_card.data();
+            dst = result_standin;
+        } else {
+            const PlanFactor &of = pl->f[st.out];
+            os.rank = (int32_t)of.var.size();
+            os.var_id = of.var.data();
+            os.card = of.card.data();
+            dst = arena_standin + pl->arena_off[st.out];
+        }
+        if (contract_plan(pl->ctx, (int)st.operands.size(), ops, &os, st.elim, 0, dst, nullptr, &pl->exec[s]) != BNPP_OK)
+            pl->exec_ok = false;
     }
 }
 
@@ -267,6 +371,7 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
         for (int id : st.operands)
             if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) live -= 8 * pl->f[id].size;
     }
+    build_exec(pl);
     *out = pl;
     return BNPP_OK;
 }
@@ -275,6 +380,7 @@ int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
 {
     if (!pl) return BNPP_OK;
     for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
+    if (pl->arena) bnpp_free(pl->ctx, pl->arena);
     delete pl;
     return BNPP_OK;
 }
@@ -339,25 +445,10 @@ int bnpp_ve_plan_step_kernel(const bnpp_ve_plan *pl, uint64_t step, char *name, 
     return BNPP_OK;
 }
 
-int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const uint32_t *obs_val, double *result_dev,
-                     double *z_dev)
+static int run_dynamic(bnpp_ve_plan *pl, const std::vector<const double *> &ptr_in, double *result_dev, double *z_dev)
 {
-    if (!pl || !result_dev) return BNPP_EINVAL;
     bnpp_ctx *ctx = pl->ctx;
-    std::vector<const double *> ptr(pl->f.size(), nullptr);
-    for (size_t i = 0; i < pl->f.size(); ++i) {
-        const PlanFactor &pf = pl->f[i];
-        if (pf.src < 0) continue;
-        uint64_t base = 0;
-        for (auto &o : pf.obs) base += (uint64_t)o.first * obs_val[o.second];
-        ptr[i] = tables_dev[pf.src] + base;
-    }
-    if (pl->steps.empty() || pl->steps.back().out != -2) {
-        int rc = fill(ctx, result_dev, 1, 1.0);   // no factor left: the scalar 1 (code/model.cpp:355)
-        if (rc != BNPP_OK) return rc;
-        if (z_dev) rc = fill(ctx, z_dev, 1, 1.0);
-        if (rc != BNPP_OK) return rc;
-    }
+    std::vector<const double *> ptr = ptr_in;
     std::vector<double *> owned(pl->f.size(), nullptr);
     int rc = BNPP_OK;
     for (size_t s = 0; s < pl->steps.size() && rc == BNPP_OK; ++s) {
@@ -400,9 +491,56 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
                 owned[id] = nullptr;
             }
     }
-    if (pl->profiling) cudaEventRecord(pl->ev[pl->steps.size()], ctx->stream);
     for (double *p : owned)
         if (p) bnpp_free(ctx, p);
+    return rc;
+}
+
+int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const uint32_t *obs_val, double *result_dev,
+                     double *z_dev)
+{
+    if (!pl || !result_dev) return BNPP_EINVAL;
+    bnpp_ctx *ctx = pl->ctx;
+    std::vector<const double *> ptr(pl->f.size(), nullptr);
+    bool aligned32 = true;
+    for (size_t i = 0; i < pl->f.size(); ++i) {
+        const PlanFactor &pf = pl->f[i];
+        if (pf.src < 0) continue;
+        uint64_t base = 0;
+        for (auto &o : pf.obs) base += (uint64_t)o.first * obs_val[o.second];
+        ptr[i] = tables_dev[pf.src] + base;
+        aligned32 = aligned32 && (reinterpret_cast<uintptr_t>(tables_dev[pf.src]) % 32 == 0);
+    }
+    if (pl->steps.empty() || pl->steps.back().out != -2) {
+        int rc = fill(ctx, result_dev, 1, 1.0);   // no factor left: the scalar 1 (code/model.cpp:355)
+        if (rc != BNPP_OK) return rc;
+        if (z_dev) rc = fill(ctx, z_dev, 1, 1.0);
+        if (rc != BNPP_OK) return rc;
+    }
+    int rc = BNPP_OK;
+    if (!pl->exec_ok || !aligned32) {
+        rc = run_dynamic(pl, ptr, result_dev, z_dev);
+    } else {
+        if (!pl->arena && pl->arena_doubles) {
+            rc = bnpp_alloc(ctx, pl->arena_doubles, &pl->arena);
+            if (rc != BNPP_OK) return rc;
+        }
+        for (size_t i = 0; i < pl->f.size(); ++i)
+            if (pl->f[i].src < 0) ptr[i] = pl->arena + pl->arena_off[i];
+        for (size_t s = 0; s < pl->steps.size() && rc == BNPP_OK; ++s) {
+            const PlanStep &st = pl->steps[s];
+            if (pl->profiling) cudaEventRecord(pl->ev[s], ctx->stream);
+            const double *in[kMaxK];
+            for (size_t q = 0; q < st.operands.size(); ++q) in[q] = ptr[st.operands[q]];
+            double *dst = st.out == -2 ? result_dev : pl->arena + pl->arena_off[st.out];
+            rc = contract_launch(ctx, pl->exec[s], in, dst, st.out == -2 ? z_dev : nullptr);
+        }
+        if (pl->profiling) {
+            pl->step_kernel.resize(pl->steps.size());
+            for (size_t s = 0; s < pl->steps.size(); ++s) pl->step_kernel[s] = pl->exec[s].name;
+        }
+    }
+    if (pl->profiling) cudaEventRecord(pl->ev[pl->steps.size()], ctx->stream);
     return rc;
 }
 

@@ -148,6 +148,13 @@ class VEPlan:
             self.ctx.L.bnpp_ve_plan_destroy(self.h)
             self.h = None
 
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:      # the plan owns a device arena: never leak it
+                self.close()
+        except Exception:
+            pass
+
 
 def capi_max_rank():
     return 64
@@ -290,10 +297,14 @@ class BN:
         sweeps = fg.update(max_sweeps, epsilon)
         return fg, sweeps
 
-    def close(self):
+    def drop_plans(self):
+        """forget every cached plan (and free its arena): the next query orders and plans from scratch"""
         for p in self._plans.values():
             p.close()
         self._plans = {}
+
+    def close(self):
+        self.drop_plans()
 
 
 def from_uai_text(ctx, text):

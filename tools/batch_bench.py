@@ -57,7 +57,7 @@ def main():
     launches = (ctx.launches - launches0) // args.iters
     t0 = time.perf_counter()
     for _ in range(args.iters):
-        bn._plans.clear()
+        bn.drop_plans()
         z = bn.partition_batch(observed, None, "mf", host_values=host)
         with torch.cuda.stream(s):
             zh = z.to("cpu", non_blocking=False)
