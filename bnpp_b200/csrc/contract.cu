@@ -321,6 +321,103 @@ __global__ void __launch_bounds__(kBlock) contract_canon(const __grid_constant__
     if (h.z) grid_sum_to(zacc, h.partials, h.ticket, h.z);   // grid-uniform: intermediates of a VE plan need no partition
 }
 
+// Transposing variant: operand `st.sk` comes through a shared-memory tile (see StageInfo).
+// The plan puts the output's 6 fastest bits on the lanes (coalesced 512-byte rows for the
+// output and the well laid-out operands) and the staged operand's fastest axes on the
+// remaining chunk bits, so the tile is a few contiguous runs of that operand.  Slots are
+// XOR-swizzled with the slot bits the lanes differ in, so a warp reads 32 distinct banks.
+template <int K, int C>
+__global__ void __launch_bounds__(kBlock, 2) contract_staged(const __grid_constant__ ParamsP2S ps)
+{
+    constexpr int U = 4, V = 2;
+    constexpr uint32_t CH = U * kBlock;
+    __shared__ double tile[4096];
+    const ParamsP2 &p = ps.b;
+    const ParamsHead &h = p.h;
+    const StageInfo &st = ps.st;
+    const int sk = st.sk;
+    uint32_t lo[U][K], olo[U], slo[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t local = threadIdx.x + u * kBlock;
+        decompose<K>(p, local, lo[u], olo[u]);
+        uint32_t sl = 0;
+        for (int f = 0; f < (int)st.ncf; ++f) sl += ((local >> st.cf[f].sh) & st.cf[f].mask) * st.cf[f].mul;
+        slo[u] = sl;
+    }
+    // Tile entry `slot = tid + 256 * i` lives at operand offset scatter(tid) + scatter(256 * i)
+    // (disjoint bits): the first term is this thread's, the second is shared by the CTA.
+    __shared__ uint32_t s_off[16];
+    uint32_t my_off = 0;
+    for (int f = 0; f < (int)st.nlf; ++f) my_off += ((threadIdx.x >> st.lf[f].sh) & st.lf[f].mask) * st.lf[f].mul;
+    if (threadIdx.x < 16) {
+        const uint32_t slot = threadIdx.x * kBlock;
+        uint32_t o = 0;
+        for (int f = 0; f < (int)st.nlf; ++f) o += ((slot >> st.lf[f].sh) & st.lf[f].mask) * st.lf[f].mul;
+        s_off[threadIdx.x] = o;
+    }
+    __syncthreads();
+    const uint32_t n_copy = (st.tile + kBlock - 1) / kBlock;
+    const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(tile);
+    const uint32_t n_chunks = (uint32_t)(h.n_items / CH);
+    double zacc = 0.0;
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        uint32_t hi[K], ohi;
+        decompose<K>(p, c * CH, hi, ohi);
+        const double *src = h.in[0];
+        uint32_t base = 0;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (k == sk) { src = h.in[k]; base = hi[k]; }
+        src += base + my_off;
+        // global -> shared without passing through registers (LDGSTS), 8 bytes per copy
+        for (uint32_t i = 0; i < n_copy; ++i) {
+            const uint32_t slot = threadIdx.x + i * kBlock;
+            if (slot < st.tile) {
+                const uint32_t dst = tile_base + 8u * (slot ^ ((slot >> st.swz) & 31u));
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + s_off[i]) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        double raw[U][K][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) raw[u][k][e] = 0.0;
+                if (k != sk) issue_loads<C, V>(h.in[k] + (hi[k] + lo[u][k]), h.sx[k], h.sl[k], h.cls[k], raw[u][k]);
+            }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double r[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+#pragma unroll
+                for (int x = 0; x < C; ++x) {
+                    const uint32_t slot = slo[u] + j * st.slot_j + x * st.slot_x;
+                    const double ts = tile[slot ^ ((slot >> st.swz) & 31u)];
+                    double a = 1.0;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const double t = (k == sk) ? ts : pick(raw[u][k], h.cls[k], j, x);
+                        a = (k == 0) ? t : __dmul_rn(a, t);
+                    }
+                    r[j] = (x == 0) ? a : __dadd_rn(r[j], a);
+                }
+            }
+            double *o = h.out + (ohi + olo[u]);
+            zacc = __dadd_rn(zacc, __dadd_rn(r[0], r[1]));
+            if (h.out_vec) *reinterpret_cast<double2 *>(o) = make_double2(r[0], r[1]);
+            else { o[0] = r[0]; o[h.sol] = r[1]; }
+        }
+        __syncthreads();
+    }
+    if (h.z) grid_sum_to(zacc, h.partials, h.ticket, h.z);
+}
+
 // Generic path: any cardinality of the eliminated variable, one output entry per item.
 template <class P, int K, bool DIV>
 __global__ void __launch_bounds__(kBlock) contract_generic(const __grid_constant__ P p)
@@ -472,6 +569,20 @@ static p2s_fn pick_p2s(int K, int C, int V, bool div, int &U)
     }
 }
 
+typedef void (*staged_fn)(const ParamsP2S);
+static staged_fn pick_staged(int K, int C)
+{
+    switch (K * 2 + (C - 1)) {
+    case 1 * 2 + 0: return contract_staged<1, 1>;
+    case 1 * 2 + 1: return contract_staged<1, 2>;
+    case 2 * 2 + 0: return contract_staged<2, 1>;
+    case 2 * 2 + 1: return contract_staged<2, 2>;
+    case 3 * 2 + 0: return contract_staged<3, 1>;
+    case 3 * 2 + 1: return contract_staged<3, 2>;
+    default: return nullptr;
+    }
+}
+
 // persistent grid: as many CTAs as are co-resident (occupancy is register-bound and differs per variant)
 template <class F>
 static uint64_t resident_ctas(bnpp_ctx *ctx, F fn)
@@ -572,7 +683,7 @@ int contract_launch(bnpp_ctx *ctx, LaunchDesc &d, const double *const *in, doubl
     h.out = out;
     h.z = z;
     void *args[1];
-    args[0] = d.p2 ? static_cast<void *>(&d.p2p) : static_cast<void *>(&d.mrp);
+    args[0] = d.p2 ? (d.staged ? static_cast<void *>(&d.p2p) : static_cast<void *>(&d.p2p.b)) : static_cast<void *>(&d.mrp);
     BNPP_CUDA(ctx, cudaLaunchKernel(d.fn, dim3(d.grid), dim3(kBlock), args, 0, ctx->stream));
     ctx->launches++;
     ctx->last_kernel = d.name;
@@ -713,6 +824,48 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
         }
     }
 
+    // ---- one transposed operand goes through shared memory -----------------------------------------
+    // binary axes innermost first: b[0] is the V bit, b[1..10] the item bits of a 1024-item chunk
+    int staged = -1;
+    std::vector<Axis> bin;
+    if (cx <= 2 && !divide && k <= 3) {
+        bool p2all = true;
+        for (const Axis &a : it) p2all = p2all && is_pow2(a.ext);
+        if (p2all) {
+            for (size_t i = it.size(); i-- > 0;)
+                for (uint32_t t = 0, e = ilog2(it[i].ext); t < e; ++t) {
+                    Axis a = it[i];
+                    a.ext = 2;
+                    a.so = it[i].so << t;
+                    for (int q = 0; q < k; ++q) a.s[q] = it[i].s[q] << t;
+                    bin.push_back(a);
+                }
+        }
+        if (bin.size() >= 11) {
+            uint64_t total = 8 * n_out;
+            for (int q = 0; q < k; ++q) total += op_bytes[q];
+            uint64_t best_bytes = 0;
+            for (int q = 0; q < k; ++q) {
+                int far = 0;   // lane-level axes (V bit + 5 lane bits) on which the operand jumps by >= 128 bytes
+                for (int a = 0; a < 6; ++a) far += (bin[a].s[q] >= 16);
+                if (far >= 4 && op_bytes[q] * 8 >= total && op_bytes[q] > best_bytes) { best_bytes = op_bytes[q]; staged = q; }
+            }
+        }
+        if (staged >= 0) {
+            // chunk bits 5..9 (b[6..10]) := the staged operand's fastest remaining axes, smallest stride first
+            for (int slot = 6; slot <= 10; ++slot) {
+                int best = -1;
+                for (size_t a = slot; a < bin.size(); ++a)
+                    if (bin[a].s[staged] != 0 && (best < 0 || bin[a].s[staged] < bin[best].s[staged])) best = (int)a;
+                if (best < 0) break;
+                const Axis ax = bin[best];
+                bin.erase(bin.begin() + best);
+                bin.insert(bin.begin() + slot, ax);
+            }
+            it.assign(bin.rbegin(), bin.rend());
+        }
+    }
+
     // merge neighbours that are contiguous in the output and in every operand
     std::vector<Axis> m;
     for (size_t i = 0; i < it.size(); ++i) {
@@ -791,8 +944,8 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
     bool p2 = true;
     for (uint32_t a = 0; a < R; ++a) p2 = p2 && is_pow2(m[a].ext);
     if (p2) {
-        ParamsP2 &p = desc->p2p;
-        memset(&p, 0, sizeof p);
+        ParamsP2 &p = desc->p2p.b;
+        memset(&desc->p2p, 0, sizeof desc->p2p);
         p.h = h;
         bool fits = true;
         for (int q = 0; q <= k && fits; ++q) {
@@ -823,8 +976,59 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
             }
             p.nf[q] = (uint8_t)nf;
         }
+        if (fits && staged >= 0 && V == 2 && h.n_items % (4 * kBlock) == 0 && h.n_items >= 4 * kBlock) {
+            // slots of the tile: the chunk-local bits the staged operand depends on, ranked by ITS stride
+            struct Loc { uint64_t stride; int item_bit; };   // item_bit: -2 = x, -1 = V bit, 0..9 = item bits
+            std::vector<Loc> loc;
+            if (C == 2 && sx[staged]) loc.push_back({sx[staged], -2});
+            for (int a = 0; a <= 10; ++a)
+                if (bin[a].s[staged]) loc.push_back({bin[a].s[staged], a - 1});
+            std::sort(loc.begin(), loc.end(), [](const Loc &x, const Loc &y) { return x.stride < y.stride; });
+            StageInfo &st = desc->p2p.st;
+            st.sk = staged;
+            st.tile = 1u << loc.size();
+            bool ok = loc.size() <= 12;
+            int rank_of_item[10];
+            for (int i = 0; i < 10; ++i) rank_of_item[i] = -1;
+            for (size_t r = 0; r < loc.size() && ok; ++r) {
+                if (loc[r].item_bit == -2) st.slot_x = 1u << r;
+                else if (loc[r].item_bit == -1) st.slot_j = 1u << r;
+                else rank_of_item[loc[r].item_bit] = (int)r;
+                // tile-load fields: runs of ranks whose strides keep doubling
+                if (st.nlf && loc[r].stride == ((uint64_t)st.lf[st.nlf - 1].mul << ilog2(st.lf[st.nlf - 1].mask + 1)))
+                    st.lf[st.nlf - 1].mask = (st.lf[st.nlf - 1].mask << 1) | 1u;
+                else if (st.nlf < 12) st.lf[st.nlf++] = Field{1u, (uint32_t)loc[r].stride, (uint32_t)r};
+                else ok = false;
+            }
+            // consumption fields: runs of item bits whose ranks are consecutive
+            for (int i = 0; i < 10 && ok; ++i) {
+                if (rank_of_item[i] < 0) continue;
+                if (st.ncf && i > 0 && rank_of_item[i - 1] >= 0 && rank_of_item[i] == rank_of_item[i - 1] + 1 &&
+                    st.cf[st.ncf - 1].sh + ilog2(st.cf[st.ncf - 1].mask + 1) == (uint32_t)i)
+                    st.cf[st.ncf - 1].mask = (st.cf[st.ncf - 1].mask << 1) | 1u;
+                else if (st.ncf < 12) st.cf[st.ncf++] = Field{1u, 1u << rank_of_item[i], (uint32_t)i};
+                else ok = false;
+            }
+            // lanes are item bits 0..4: swizzle with the lowest slot bit any of them drives (if it is high enough)
+            int low = 32;
+            for (int i = 0; i < 5; ++i)
+                if (rank_of_item[i] >= 0 && rank_of_item[i] < low) low = rank_of_item[i];
+            st.swz = (low >= 5 && low < 32) ? (uint32_t)low : 31u;
+            staged_fn fn = ok ? pick_staged(k, C) : nullptr;
+            if (fn) {
+                desc->p2 = true;
+                desc->staged = true;
+                uint64_t blocks = h.n_items / (4 * kBlock);
+                const uint64_t cap = resident_ctas(ctx, fn);
+                if (blocks > cap) blocks = cap;
+                describe(desc, p.h, reinterpret_cast<const void *>(fn), blocks, staged == 0 ? "staged0" : (staged == 1 ? "staged1" : "staged2"),
+                         k, C, V, 4, false, false, R);
+                return BNPP_OK;
+            }
+        }
         if (fits) {
             desc->p2 = true;
+            desc->staged = false;
             if (!generic && plan_launch_p2s(ctx, desc, p, k, C, V, divide != 0, R)) return BNPP_OK;
             return plan_launch(ctx, desc, p, k, C, V, divide != 0, generic, "p2", R);
         }

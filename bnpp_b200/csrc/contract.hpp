@@ -47,15 +47,34 @@ struct ParamsP2 {
     Field f[kMaxK + 1][kMaxF];
 };
 
+// One operand whose fastest axes are slow axes of the output ("transposed" layout) is not
+// gathered from global memory lane by lane: each CTA chunk first copies the tile of it that
+// the chunk needs into shared memory, reading along the operand's OWN fastest axes.
+//   slot -> operand offset : sum_f ((slot  >> sh) & mask) * mul   over lf   (tile load)
+//   item -> slot           : sum_f ((local >> sh) & mask) * mul   over cf   (consumption)
+struct StageInfo {
+    int32_t sk;                 // staged operand
+    uint32_t tile;              // tile entries (power of two, <= 4096)
+    uint32_t slot_j, slot_x;    // slot stride of the V bit and of the eliminated variable (0 = independent)
+    uint32_t swz;               // bank swizzle: phys = slot ^ ((slot >> swz) & 31); the lanes differ in slot bits >= swz
+    uint8_t nlf, ncf;
+    Field lf[12], cf[12];
+};
+struct ParamsP2S {
+    ParamsP2 b;
+    StageInfo st;
+};
+
 struct LaunchDesc {
     const void *fn = nullptr;
     unsigned grid = 0;
     bool p2 = false;
+    bool staged = false;
     int k = 0;
-    ParamsP2 p2p;
+    ParamsP2S p2p;              // .b is the plain power-of-two block
     ParamsMR mrp;
     std::string name;
-    ParamsHead &head() { return p2 ? p2p.h : mrp.h; }
+    ParamsHead &head() { return p2 ? p2p.b.h : mrp.h; }
 };
 
 int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope, int64_t elim_var,

@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--only", default=None, help="kind filter")
     ap.add_argument("--no-reverse", action="store_true")
+    ap.add_argument("--mixed", action="store_true", help="the mixed-cardinality case of SURVEY 8d: cards cycle 2,3,4,5 over 16 axes (2.07e8 union entries)")
     args = ap.parse_args()
     ctx = capi.Context(0)
     peak, how = peak_gbs()
@@ -66,6 +67,41 @@ def main():
         return cache[key]
 
     rows = []
+    if args.mixed:
+        cards = [2, 3, 4, 5] * 4
+        allv = list(range(16))
+        import numpy as np
+        for k in (0, 1, 6, 15):
+            sa, sb = allv, [v for v in allv if v != (k + 3) % 16]      # B lacks one axis, keeps the eliminated one
+            A = DeviceFactor.empty(ctx, sa, [cards[v] for v in sa])
+            B = DeviceFactor.empty(ctx, sb, [cards[v] for v in sb])
+            A.buf[:-1] = torch.rand(A.size, generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+            B.buf[:-1] = torch.rand(B.size, generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+            out_scope = [v for v in allv if v != k]
+            out = DeviceFactor.empty(ctx, out_scope, [cards[v] for v in out_scope])
+            ops = [(A.ptr, sa, A.cards, None), (B.ptr, sb, B.cards, None)]
+            torch.cuda.synchronize()
+            s_ = ctx.torch_stream
+            times = []
+            for it in range(args.iters + 2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(s_)
+                ctx.product_sum_out(ops, out_scope, out.cards, k, out.ptr, out.zptr)
+                e1.record(s_)
+                e1.synchronize()
+                if it >= 2:
+                    times.append(e0.elapsed_time(e1))
+            ms = sum(times) / len(times)
+            nbytes = 8 * (A.size + B.size + out.size)
+            print("mixed  k=%2d card=%d  %8.3f ms  %8.1f GB/s  %5.1f%% of %s peak  %.3e entries/s  %s"
+                  % (k, cards[k], ms, nbytes / ms / 1e6, 100 * nbytes / ms / 1e6 / peak, how, A.size / ms * 1e3,
+                     ctx.last_launch()[0]), flush=True)
+            rows.append({"kind": "mixed", "k": k, "card": cards[k], "ms": ms, "GBs": nbytes / ms / 1e6,
+                         "frac": nbytes / ms / 1e6 / peak, "kernel": ctx.last_launch()[0]})
+            del A, B, out
+        if args.json:
+            json.dump({"peak_gbs": peak, "peak_kind": how, "rows": rows}, open(args.json, "w"), indent=1)
+        return
     for kind, k, rev, sa, sb in shapes(args.bits):
         if args.only and kind != args.only:
             continue
