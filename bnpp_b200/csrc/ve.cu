@@ -62,6 +62,13 @@ struct bnpp_ve_plan {
     uint64_t arena_doubles = 0;
     double *arena = nullptr;
     bool exec_ok = false;
+    // the whole schedule as one CUDA graph (a chain of kernel nodes): a replay is one
+    // cudaGraphLaunch; only nodes whose pointers moved (other evidence values) are re-parameterised
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<cudaGraphNode_t> nodes;
+    bool use_graph = true;
+    uint64_t runs = 0;                      // the graph is built on the second run: a one-shot plan never pays for it
     bool profiling = false;
     std::vector<cudaEvent_t> ev;
     std::vector<float> step_ms;
@@ -380,6 +387,8 @@ int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
 {
     if (!pl) return BNPP_OK;
     for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
+    if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
+    if (pl->graph) cudaGraphDestroy(pl->graph);
     if (pl->arena) bnpp_free(pl->ctx, pl->arena);
     delete pl;
     return BNPP_OK;
@@ -527,13 +536,50 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
         }
         for (size_t i = 0; i < pl->f.size(); ++i)
             if (pl->f[i].src < 0) ptr[i] = pl->arena + pl->arena_off[i];
+        const bool graphed = pl->use_graph && !pl->profiling && pl->steps.size() > 1 && pl->runs >= 1;
+        bool fresh = false;
+        if (graphed && !pl->graph_exec) {
+            if (cudaGraphCreate(&pl->graph, 0) != cudaSuccess) pl->use_graph = false;
+            pl->nodes.assign(pl->steps.size(), nullptr);
+            fresh = true;
+        }
         for (size_t s = 0; s < pl->steps.size() && rc == BNPP_OK; ++s) {
             const PlanStep &st = pl->steps[s];
             if (pl->profiling) cudaEventRecord(pl->ev[s], ctx->stream);
             const double *in[kMaxK];
             for (size_t q = 0; q < st.operands.size(); ++q) in[q] = ptr[st.operands[q]];
             double *dst = st.out == -2 ? result_dev : pl->arena + pl->arena_off[st.out];
-            rc = contract_launch(ctx, pl->exec[s], in, dst, st.out == -2 ? z_dev : nullptr);
+            double *z = st.out == -2 ? z_dev : nullptr;
+            if (!(graphed && pl->use_graph)) {
+                rc = contract_launch(ctx, pl->exec[s], in, dst, z);
+                continue;
+            }
+            LaunchDesc &d = pl->exec[s];
+            ParamsHead &h = d.head();
+            bool moved = fresh || h.out != dst || h.z != z;
+            for (size_t q = 0; q < st.operands.size(); ++q) moved = moved || h.in[q] != in[q];
+            if (!moved) continue;
+            for (size_t q = 0; q < st.operands.size(); ++q) h.in[q] = in[q];
+            h.out = dst;
+            h.z = z;
+            void *args[1];
+            args[0] = d.p2 ? (d.staged ? static_cast<void *>(&d.p2p) : static_cast<void *>(&d.p2p.b)) : static_cast<void *>(&d.mrp);
+            cudaKernelNodeParams kp;
+            memset(&kp, 0, sizeof kp);
+            kp.func = const_cast<void *>(d.fn);
+            kp.gridDim = dim3(d.grid);
+            kp.blockDim = dim3(kBlock);
+            kp.kernelParams = args;
+            cudaError_t e;
+            if (fresh) e = cudaGraphAddKernelNode(&pl->nodes[s], pl->graph, s ? &pl->nodes[s - 1] : nullptr, s ? 1 : 0, &kp);
+            else e = cudaGraphExecKernelNodeSetParams(pl->graph_exec, pl->nodes[s], &kp);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "CUDA graph node");
+        }
+        if (graphed && pl->use_graph && rc == BNPP_OK) {
+            if (fresh) BNPP_CUDA(ctx, cudaGraphInstantiate(&pl->graph_exec, pl->graph, 0));
+            BNPP_CUDA(ctx, cudaGraphLaunch(pl->graph_exec, ctx->stream));
+            ctx->launches += pl->steps.size();
+            ctx->last_kernel = pl->exec.back().name;
         }
         if (pl->profiling) {
             pl->step_kernel.resize(pl->steps.size());
@@ -541,6 +587,7 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
         }
     }
     if (pl->profiling) cudaEventRecord(pl->ev[pl->steps.size()], ctx->stream);
+    pl->runs++;
     return rc;
 }
 
