@@ -31,83 +31,133 @@ struct BOperand {
 struct BParams {
     BOperand op[kMaxK];
     double *out;                            // [n_out][nb]
-    const uint8_t *ev;                      // [nb][n_obs] evidence values of this launch's sets
-    uint32_t n_obs, nb, n_out, cx, R;
+    const uint8_t *ev;                      // [n_obs][ev_stride] evidence values, set index fastest (column of this slice)
+    uint32_t ev_stride;
+    uint32_t n_obs, nb, n_out, cx;
+    uint32_t oc, n_chunks;                  // a thread walks `oc` consecutive output entries for its evidence sets
+    const uint32_t *offtab;                 // [K][n_out] operand offset of output entry o (built by the plan, L1-resident)
     FastDiv nbdiv;
-    FastDiv div[kMaxR];
-    uint32_t s[kMaxK][kMaxR];
 };
 
-template <int K>
+// A thread owns VB evidence sets (2 when the slice is even: 16-byte accesses on the batched
+// tables) and walks `oc` consecutive output entries for them.  What depends only on the sets
+// -- the evidence base of every resident CPT -- is computed once per thread, what depends only
+// on the output entry -- operand offsets -- comes from a small table that a warp reads as one
+// broadcast (all lanes share the entry, the batch being the fastest axis).
+template <int K, int VB>
 __global__ void __launch_bounds__(kBlock) contract_batched(const __grid_constant__ BParams p)
 {
-    const uint64_t total = (uint64_t)p.n_out * p.nb;
+    const uint32_t nbv = p.nb / VB;
+    const uint64_t total = (uint64_t)p.n_chunks * nbv;
     const uint64_t step = (uint64_t)gridDim.x * kBlock;
     for (uint64_t idx = (uint64_t)blockIdx.x * kBlock + threadIdx.x; idx < total; idx += step) {
-        // idx = o * nb + b with the batch fastest
-        uint32_t o, b;
-        if (p.nb == 1) { o = (uint32_t)idx; b = 0; }
-        else if (total < (1ull << 32)) { o = fastdiv((uint32_t)idx, p.nbdiv); b = (uint32_t)idx - o * p.nb; }
-        else { o = (uint32_t)(idx / p.nb); b = (uint32_t)(idx - (uint64_t)o * p.nb); }
-        uint32_t off[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) off[k] = 0;
-        uint32_t rem = o;
-        for (int a = (int)p.R - 1; a > 0; --a) {
-            const uint32_t q = fastdiv(rem, p.div[a]);
-            const uint32_t d = rem - q * p.div[a].d;
-            rem = q;
-#pragma unroll
-            for (int k = 0; k < K; ++k) off[k] += d * p.s[k][a];
-        }
-        if (p.R > 0) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) off[k] += rem * p.s[k][0];
-        }
-        const uint8_t *ev = p.ev + (uint64_t)b * p.n_obs;
-        const double *src[K];
-        uint64_t xs[K];
+        uint32_t chunk, bv;
+        if (nbv == 1) { chunk = (uint32_t)idx; bv = 0; }
+        else if (total < (1ull << 32)) { chunk = fastdiv((uint32_t)idx, p.nbdiv); bv = (uint32_t)idx - chunk * nbv; }
+        else { chunk = (uint32_t)(idx / nbv); bv = (uint32_t)(idx - (uint64_t)chunk * nbv); }
+        const uint32_t b = bv * VB;
+        const double *base[K][VB];
+        uint64_t xs[K], os[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const BOperand &op = p.op[k];
             if (op.batched) {
-                src[k] = op.ptr + ((uint64_t)off[k] * p.nb + b);
+                base[k][0] = op.ptr + b;
+                if (VB == 2) base[k][VB - 1] = base[k][0] + 1;
                 xs[k] = (uint64_t)op.sx * p.nb;
+                os[k] = p.nb;
             } else {
-                uint32_t base = off[k];
-                for (uint32_t j = 0; j < op.nobs; ++j) base += op.ostride[j] * ev[op.oidx[j]];
-                src[k] = op.ptr + base;
+                uint32_t e[VB];
+#pragma unroll
+                for (int v = 0; v < VB; ++v) e[v] = 0;
+                for (uint32_t j = 0; j < op.nobs; ++j) {
+                    const uint8_t *col = p.ev + (uint64_t)op.oidx[j] * p.ev_stride + b;   // neighbouring threads, neighbouring bytes
+#pragma unroll
+                    for (int v = 0; v < VB; ++v) e[v] += op.ostride[j] * col[v];
+                }
+#pragma unroll
+                for (int v = 0; v < VB; ++v) base[k][v] = op.ptr + e[v];
                 xs[k] = op.sx;
+                os[k] = 1;
             }
         }
-        double acc = 0.0;
-        for (uint32_t x = 0; x < p.cx; ++x) {
-            double v = ld1(src[0] + x * xs[0]);
+        const uint32_t o_end = min(p.n_out, (chunk + 1) * p.oc);
+        for (uint32_t o = chunk * p.oc; o < o_end; ++o) {
+            const double *src[K][VB];
 #pragma unroll
-            for (int k = 1; k < K; ++k) v = __dmul_rn(v, ld1(src[k] + x * xs[k]));
-            acc = (x == 0) ? v : __dadd_rn(acc, v);
+            for (int k = 0; k < K; ++k) {
+                const uint64_t off = (uint64_t)__ldg(p.offtab + (uint64_t)k * p.n_out + o) * os[k];
+#pragma unroll
+                for (int v = 0; v < VB; ++v) src[k][v] = base[k][v] + off;
+            }
+            double acc[VB];
+            for (uint32_t x = 0; x < p.cx; ++x) {
+                double v[VB];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    double t[VB];
+                    if (VB == 2 && p.op[k].batched) {
+                        const double2 d2 = ld2(src[k][0] + x * xs[k]);
+                        t[0] = d2.x;
+                        t[VB - 1] = d2.y;
+                    } else {
+#pragma unroll
+                        for (int w = 0; w < VB; ++w) t[w] = ld1(src[k][w] + x * xs[k]);
+                    }
+#pragma unroll
+                    for (int w = 0; w < VB; ++w) v[w] = (k == 0) ? t[w] : __dmul_rn(v[w], t[w]);
+                }
+#pragma unroll
+                for (int w = 0; w < VB; ++w) acc[w] = (x == 0) ? v[w] : __dadd_rn(acc[w], v[w]);
+            }
+            double *dst = p.out + ((uint64_t)o * p.nb + b);
+            if (VB == 2) *reinterpret_cast<double2 *>(dst) = make_double2(acc[0], acc[VB - 1]);
+            else dst[0] = acc[0];
         }
-        p.out[idx] = acc;
     }
+}
+
+// [nb][n_obs] (one row per evidence set, as the caller has it) -> [n_obs][nb]
+__global__ void transpose_evidence(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint32_t nb, uint32_t n_obs)
+{
+    const uint64_t n = (uint64_t)nb * n_obs;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)(i / nb), b = (uint32_t)(i - (uint64_t)j * nb);
+        out[i] = in[(uint64_t)b * n_obs + j];
+    }
+}
+
+int transpose_evidence_launch(bnpp_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t nb, uint32_t n_obs)
+{
+    if (!nb || !n_obs) return BNPP_OK;
+    const uint64_t n = (uint64_t)nb * n_obs;
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    transpose_evidence<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, nb, n_obs);
+    BNPP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return BNPP_OK;
 }
 
 typedef void (*batched_fn)(const BParams);
 
-static batched_fn pick_batched(int K)
+template <int VB>
+static batched_fn pick_batched_v(int K)
 {
     switch (K) {
-    case 1: return contract_batched<1>;
-    case 2: return contract_batched<2>;
-    case 3: return contract_batched<3>;
-    case 4: return contract_batched<4>;
-    case 5: return contract_batched<5>;
-    default: return contract_batched<6>;
+    case 1: return contract_batched<1, VB>;
+    case 2: return contract_batched<2, VB>;
+    case 3: return contract_batched<3, VB>;
+    case 4: return contract_batched<4, VB>;
+    case 5: return contract_batched<5, VB>;
+    default: return contract_batched<6, VB>;
     }
 }
 
 int contract_batched_step(bnpp_ctx *ctx, int k, const BatchedOperandDesc *ops, const std::vector<uint32_t> &out_var,
                           const std::vector<uint32_t> &out_card, int64_t elim, uint32_t nb, const uint8_t *ev_dev,
-                          uint32_t n_obs, double *out_dev)
+                          uint32_t ev_stride, uint32_t n_obs, double *out_dev, std::vector<uint32_t> *offtab_host,
+                          uint32_t **offtab_dev)
 {
     if (k < 1 || k > kMaxK) return fail(ctx, BNPP_ERANK, "batched step: operand count");
     BParams p;
@@ -149,40 +199,55 @@ int contract_batched_step(bnpp_ctx *ctx, int k, const BatchedOperandDesc *ops, c
             p.op[q].oidx[j] = (uint32_t)(*op.obs)[j].second;
         }
     }
-    // merge contiguous axes (output dense, so only the operands decide)
-    std::vector<Ax> m;
-    for (int i = 0; i < wr; ++i) {
-        if (axes[i].ext == 1) continue;
-        if (!m.empty()) {
-            Ax &o = m.back();
-            bool ok = true;
-            for (int q = 0; q < k && ok; ++q) ok = (o.s[q] == axes[i].s[q] * axes[i].ext);
-            if (ok) {
-                o.ext *= axes[i].ext;
-                for (int q = 0; q < k; ++q) o.s[q] = axes[i].s[q];
-                continue;
+    // operand offset of every output entry (row-major odometer over the output axes)
+    std::vector<uint32_t> &tab = *offtab_host;
+    if (tab.empty()) {
+        tab.assign((size_t)k * n_out, 0);
+        std::vector<uint32_t> digit(wr, 0);
+        for (uint64_t o = 0; o < n_out; ++o) {
+            for (int q = 0; q < k; ++q) {
+                uint64_t off = 0;
+                for (int i = 0; i < wr; ++i) off += (uint64_t)digit[i] * axes[i].s[q];
+                tab[(size_t)q * n_out + o] = (uint32_t)off;
+            }
+            for (int i = wr - 1; i >= 0; --i) {
+                if (++digit[i] < axes[i].ext) break;
+                digit[i] = 0;
             }
         }
-        m.push_back(axes[i]);
     }
-    if ((int)m.size() > kMaxR) return fail(ctx, BNPP_ERANK, "batched step: too many axes");
-    p.R = (uint32_t)m.size();
-    for (uint32_t a = 0; a < p.R; ++a) {
-        p.div[a] = make_fastdiv(m[a].ext);
-        for (int q = 0; q < k; ++q) p.s[q][a] = (uint32_t)m[a].s[q];
+    if (!*offtab_dev) {
+        double *store = nullptr;
+        const int rc = bnpp_alloc(ctx, (tab.size() + 1) / 2 + 1, &store);
+        if (rc != BNPP_OK) return rc;
+        *offtab_dev = reinterpret_cast<uint32_t *>(store);
+        BNPP_CUDA(ctx, cudaMemcpyAsync(*offtab_dev, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     }
+    p.offtab = *offtab_dev;
     p.out = out_dev;
     p.ev = ev_dev;
+    p.ev_stride = ev_stride;
     p.n_obs = n_obs;
     p.nb = nb;
-    p.nbdiv = make_fastdiv(nb > 1 ? nb : 2);
+    // two sets per thread when every batched table keeps 16-byte alignment: even slice, aligned bases
+    int vb = (nb % 2 == 0 && reinterpret_cast<uintptr_t>(out_dev) % 16 == 0) ? 2 : 1;
+    for (int q = 0; q < k && vb == 2; ++q)
+        if (ops[q].batched && reinterpret_cast<uintptr_t>(ops[q].ptr) % 16 != 0) vb = 1;
+    p.nbdiv = make_fastdiv(nb / vb > 1 ? nb / vb : 2);
+    // enough threads to fill the machine, as many output entries per thread as that leaves
+    const uint64_t want_threads = (uint64_t)ctx->sm_count * 2048;
+    uint64_t oc = (n_out * (nb / vb)) / want_threads;
+    if (oc < 1) oc = 1;
+    if (oc > 16) oc = 16;
+    p.oc = (uint32_t)oc;
+    p.n_chunks = (uint32_t)((n_out + oc - 1) / oc);
     p.n_out = (uint32_t)n_out;
     p.cx = cx;
-    const uint64_t total = n_out * nb;
+    const uint64_t total = (uint64_t)p.n_chunks * (nb / vb);
     uint64_t blocks = (total + kBlock - 1) / kBlock;
     const uint64_t cap = (uint64_t)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    pick_batched(k)<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(p);
+    (vb == 2 ? pick_batched_v<2>(k) : pick_batched_v<1>(k))<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(p);
     BNPP_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return BNPP_OK;

@@ -20,6 +20,10 @@ struct BatchedOperandDesc {
 
 int contract_batched_step(bnpp_ctx *ctx, int k, const BatchedOperandDesc *ops, const std::vector<uint32_t> &out_var,
                           const std::vector<uint32_t> &out_card, int64_t elim, uint32_t nb, const uint8_t *ev_dev,
-                          uint32_t n_obs, double *out_dev);
+                          uint32_t ev_stride, uint32_t n_obs, double *out_dev, std::vector<uint32_t> *offtab_host,
+                          uint32_t **offtab_dev);
+// ev_dev above is COLUMN-major ([n_obs][ev_stride], first set of the slice at ev_dev[0]); this turns the
+// caller's row-major [nb][n_obs] matrix into it
+int transpose_evidence_launch(bnpp_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t nb, uint32_t n_obs);
 
 }  // namespace bnpp

@@ -67,6 +67,9 @@ struct bnpp_ve_plan {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     std::vector<cudaGraphNode_t> nodes;
+    // batched replay: per-step operand-offset tables (host copy + device copy, built on first use)
+    std::vector<std::vector<uint32_t>> offtab_host;
+    std::vector<uint32_t *> offtab_dev;
     bool use_graph = true;
     uint64_t runs = 0;                      // the graph is built on the second run: a one-shot plan never pays for it
     bool profiling = false;
@@ -390,6 +393,8 @@ int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
     if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
     if (pl->graph) cudaGraphDestroy(pl->graph);
     if (pl->arena) bnpp_free(pl->ctx, pl->arena);
+    for (uint32_t *t : pl->offtab_dev)
+        if (t) bnpp_free(pl->ctx, reinterpret_cast<double *>(t));
     delete pl;
     return BNPP_OK;
 }
@@ -610,6 +615,16 @@ int bnpp_ve_plan_run_batched(bnpp_ve_plan *pl, const double *const *tables_dev, 
     static const std::vector<int64_t> dense;
     static const std::vector<std::pair<int64_t, int>> no_obs;
     int rc = BNPP_OK;
+    // evidence columns contiguous over the sets: every thread of a warp then reads neighbouring bytes
+    double *evt_store = nullptr;
+    rc = bnpp_alloc(ctx, ((uint64_t)nb * (n_obs ? n_obs : 1) + 7) / 8 + 1, &evt_store);
+    if (rc != BNPP_OK) return rc;
+    uint8_t *evt = reinterpret_cast<uint8_t *>(evt_store);
+    if (pl->offtab_host.size() != pl->steps.size()) {
+        pl->offtab_host.assign(pl->steps.size(), std::vector<uint32_t>());
+        pl->offtab_dev.assign(pl->steps.size(), nullptr);
+    }
+    rc = transpose_evidence_launch(ctx, ev_dev, evt, nb, n_obs);
     for (uint32_t b0 = 0; b0 < nb && rc == BNPP_OK; b0 += slice) {
         const uint32_t cur = std::min(slice, nb - b0);
         std::vector<double *> owned(pl->f.size(), nullptr);
@@ -639,8 +654,8 @@ int bnpp_ve_plan_run_batched(bnpp_ve_plan *pl, const double *const *tables_dev, 
                 if (rc != BNPP_OK) break;
                 dst = owned[st.out];
             }
-            rc = contract_batched_step(ctx, (int)st.operands.size(), ops, *ov, *oc, st.elim, cur,
-                                       ev_dev + (uint64_t)b0 * n_obs, n_obs, dst);
+            rc = contract_batched_step(ctx, (int)st.operands.size(), ops, *ov, *oc, st.elim, cur, evt + b0, nb, n_obs, dst,
+                                       &pl->offtab_host[s], &pl->offtab_dev[s]);
             for (int id : st.operands)
                 if (owned[id] && pl->f[id].last_use == (int)s) {
                     bnpp_free(ctx, owned[id]);
@@ -651,6 +666,7 @@ int bnpp_ve_plan_run_batched(bnpp_ve_plan *pl, const double *const *tables_dev, 
             if (p) bnpp_free(ctx, p);
         if (pl->steps.empty() || pl->steps.back().out != -2) rc = fill(ctx, result_dev + b0, cur, 1.0);
     }
+    bnpp_free(ctx, evt_store);
     return rc;
 }
 

@@ -55,6 +55,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
     launches = (ctx.launches - launches0) // args.iters
+    plan_bytes = list(bn._plans.values())[0].bytes      # 8 * (sum #operands + #out) per evidence set (CPT reads included)
     t0 = time.perf_counter()
     for _ in range(args.iters):
         bn.drop_plans()
@@ -70,7 +71,9 @@ def main():
         out = {"metric": "VE PR queries/sec", "config": "config 5: %d evidence sets, 500-variable BN (W=6 K=3 seed=11), 20 observed ids fixed" % args.sets,
                "n_gpus": world, "value": args.sets / ms * 1e3, "unit": "queries/s", "ms_per_batch": ms,
                "e2e": {"value": args.sets / e2e_ms * 1e3, "ms_per_batch": e2e_ms, "h2d_bytes": host.numel() * world, "d2h_bytes": 8 * args.sets},
-               "launches_per_batch": launches, "sample_Z": zh[:3].tolist()}
+               "launches_per_batch": launches, "sample_Z": zh[:3].tolist(),
+               "algorithmic_GB_per_batch_per_rank": plan_bytes * (hi - lo) / 1e9,
+               "GBs_per_rank": plan_bytes * (hi - lo) / ms / 1e6}
         print(json.dumps(out))
         if args.json:
             json.dump(out, open(args.json, "w"))
