@@ -144,6 +144,128 @@ __device__ __forceinline__ double pick(const double (&r)[4], uint8_t cls, int j,
     }
 }
 
+// ---- per-operand dispatch hoisted over the thread's U items -----------------------------------
+// One switch per operand and phase (not per element): phase 1 issues the loads of all U items of
+// operand k inside the case of its class; phase 2 multiplies the accumulators IN PLACE inside
+// the case, so no loaded value is ever copied or selected at run time.
+template <int C, int V, int U>
+__device__ __forceinline__ void issue_loads_all(const double *__restrict__ base, const uint32_t (&off)[U], uint32_t sx,
+                                                uint32_t sl, uint8_t cls, double (&r)[U][4])
+{
+    switch (cls) {
+    case LC_BCAST:
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u][0] = ld1(base + off[u]);
+        break;
+    case LC_VX_B:
+    case LC_VL_B:
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double2 a = ld2(base + off[u]);
+            r[u][0] = a.x; r[u][1] = a.y;
+        }
+        break;
+    case LC_VX:
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double2 a = ld2(base + off[u]), b = ld2(base + off[u] + sl);
+            r[u][0] = a.x; r[u][1] = a.y; r[u][2] = b.x; r[u][3] = b.y;
+        }
+        break;
+    case LC_VL:
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double2 a = ld2(base + off[u]), b = ld2(base + off[u] + sx);
+            r[u][0] = a.x; r[u][1] = a.y; r[u][2] = b.x; r[u][3] = b.y;
+        }
+        break;
+    case LC_V4:
+    case LC_V4T:
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double4_t a = ld4(base + off[u]);
+            r[u][0] = a.x; r[u][1] = a.y; r[u][2] = a.z; r[u][3] = a.w;
+        }
+        break;
+    case LC_S_X:
+#pragma unroll
+        for (int u = 0; u < U; ++u) { r[u][0] = ld1(base + off[u]); r[u][1] = ld1(base + off[u] + sx); }
+        break;
+    case LC_S_L:
+#pragma unroll
+        for (int u = 0; u < U; ++u) { r[u][0] = ld1(base + off[u]); r[u][1] = ld1(base + off[u] + sl); }
+        break;
+    default:
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double *q = base + off[u];
+            r[u][0] = ld1(q); r[u][1] = ld1(q + sx); r[u][2] = ld1(q + sl); r[u][3] = ld1(q + sl + sx);
+        }
+        break;
+    }
+}
+
+// acc[u][j][x] (op)= element (j, x) of operand k's micro-tile;  IDX: 0 -> r[0], 1 -> r[x], 2 -> r[j], 3 -> r[2x+j], 4 -> r[2j+x]
+template <int C, int V, int U, bool FIRST, bool DIV, int IDX>
+__device__ __forceinline__ void apply_idx(const double (&r)[U][4], double (&acc)[U][V][C], bool &zero_div)
+{
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+#pragma unroll
+            for (int x = 0; x < C; ++x) {
+                const int e = IDX == 0 ? 0 : (IDX == 1 ? x : (IDX == 2 ? j : (IDX == 3 ? 2 * x + j : 2 * j + x)));
+                const double t = r[u][e];
+                if (FIRST) acc[u][j][x] = t;
+                else if (DIV) { zero_div |= (t == 0.0); acc[u][j][x] = __ddiv_rn(acc[u][j][x], t); }
+                else acc[u][j][x] = __dmul_rn(acc[u][j][x], t);
+            }
+}
+
+template <int C, int V, int U, bool FIRST, bool DIV>
+__device__ __forceinline__ void apply_all(const double (&r)[U][4], uint8_t cls, double (&acc)[U][V][C], bool &zero_div)
+{
+    switch (cls) {
+    case LC_BCAST: apply_idx<C, V, U, FIRST, DIV, 0>(r, acc, zero_div); break;
+    case LC_VX_B:
+    case LC_S_X: apply_idx<C, V, U, FIRST, DIV, 1>(r, acc, zero_div); break;
+    case LC_VL_B:
+    case LC_S_L: apply_idx<C, V, U, FIRST, DIV, 2>(r, acc, zero_div); break;
+    case LC_VL:
+    case LC_V4T: apply_idx<C, V, U, FIRST, DIV, 3>(r, acc, zero_div); break;
+    default: apply_idx<C, V, U, FIRST, DIV, 4>(r, acc, zero_div); break;
+    }
+}
+
+template <int K, int C, int V, int U, bool DIV, int k0 = 0>
+struct ApplyOperands {
+    static __device__ __forceinline__ void run(const double (&raw)[K][U][4], const uint8_t *cls, double (&acc)[U][V][C],
+                                               bool &zero_div, int skip)
+    {
+        if (k0 != skip) apply_all<C, V, U, k0 == 0, DIV>(raw[k0], cls[k0], acc, zero_div);
+        ApplyOperands<K, C, V, U, DIV, k0 + 1>::run(raw, cls, acc, zero_div, skip);
+    }
+};
+template <int K, int C, int V, int U, bool DIV>
+struct ApplyOperands<K, C, V, U, DIV, K> {
+    static __device__ __forceinline__ void run(const double (&)[K][U][4], const uint8_t *, double (&)[U][V][C], bool &, int) {}
+};
+
+template <int K, int C, int V, int U, int k0 = 0>
+struct ApplyOperandsStaged {
+    static __device__ __forceinline__ void run(const double (&raw)[K][U][4], const uint8_t *cls, double (&acc)[U][V][C],
+                                               bool &zero_div, int skip)
+    {
+        if (k0 != skip) apply_all<C, V, U, false, false>(raw[k0], cls[k0], acc, zero_div);
+        ApplyOperandsStaged<K, C, V, U, k0 + 1>::run(raw, cls, acc, zero_div, skip);
+    }
+};
+template <int K, int C, int V, int U>
+struct ApplyOperandsStaged<K, C, V, U, K> {
+    static __device__ __forceinline__ void run(const double (&)[K][U][4], const uint8_t *, double (&)[U][V][C], bool &, int) {}
+};
+
 // Fast path: eliminated variable binary (C = 2) or absent (C = 1).  Each CTA walks
 // chunks of U * kBlock consecutive items.  Phase 1 issues the loads of all K operands of
 // all U items of a thread back to back; nothing reads a loaded register until phase 2,
@@ -225,31 +347,24 @@ __global__ void __launch_bounds__(kBlock) contract_fast_p2s(const __grid_constan
     for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         uint32_t hi[K], ohi;
         decompose<K>(p, c * CH, hi, ohi);
-        double raw[U][K][4];
+        double raw[K][U][4];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+        for (int k = 0; k < K; ++k) {
+            uint32_t off[U];
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) raw[u][k][e] = 0.0;
-                issue_loads<C, V>(h.in[k] + (hi[k] + lo[u][k]), h.sx[k], h.sl[k], h.cls[k], raw[u][k]);
-            }
+            for (int u = 0; u < U; ++u) off[u] = hi[k] + lo[u][k];
+            issue_loads_all<C, V, U>(h.in[k], off, h.sx[k], h.sl[k], h.cls[k], raw[k]);
+        }
+        double acc[U][V][C];
+        ApplyOperands<K, C, V, U, DIV>::run(raw, h.cls, acc, zero_div, -1);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             double r[V];
 #pragma unroll
             for (int j = 0; j < V; ++j) {
+                r[j] = acc[u][j][0];
 #pragma unroll
-                for (int x = 0; x < C; ++x) {
-                    double a = pick(raw[u][0], h.cls[0], j, x);
-#pragma unroll
-                    for (int k = 1; k < K; ++k) {
-                        const double t = pick(raw[u][k], h.cls[k], j, x);
-                        if (DIV) { zero_div |= (t == 0.0); a = __ddiv_rn(a, t); }
-                        else a = __dmul_rn(a, t);
-                    }
-                    r[j] = (x == 0) ? a : __dadd_rn(r[j], a);
-                }
+                for (int x = 1; x < C; ++x) r[j] = __dadd_rn(r[j], acc[u][j][x]);
             }
             double *o = h.out + (ohi + olo[u]);
             if (V == 2) {
@@ -379,39 +494,38 @@ __global__ void __launch_bounds__(kBlock, 2) contract_staged(const __grid_consta
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        double raw[U][K][4];
+        double raw[K][U][4];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (k == sk) continue;
+            uint32_t off[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) off[u] = hi[k] + lo[u][k];
+            issue_loads_all<C, V, U>(h.in[k], off, h.sx[k], h.sl[k], h.cls[k], raw[k]);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        // the staged operand first (acc = its tile entries), then the others multiply in place
+        double acc[U][V][C];
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) raw[u][k][e] = 0.0;
-                if (k != sk) issue_loads<C, V>(h.in[k] + (hi[k] + lo[u][k]), h.sx[k], h.sl[k], h.cls[k], raw[u][k]);
-            }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            double r[V];
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
+            for (int j = 0; j < V; ++j)
 #pragma unroll
                 for (int x = 0; x < C; ++x) {
                     const uint32_t slot = slo[u] + j * st.slot_j + x * st.slot_x;
-                    const double ts = tile[slot ^ ((slot >> st.swz) & 31u)];
-                    double a = 1.0;
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const double t = (k == sk) ? ts : pick(raw[u][k], h.cls[k], j, x);
-                        a = (k == 0) ? t : __dmul_rn(a, t);
-                    }
-                    r[j] = (x == 0) ? a : __dadd_rn(r[j], a);
+                    acc[u][j][x] = tile[slot ^ ((slot >> st.swz) & 31u)];
                 }
-            }
+        bool zd = false;
+        ApplyOperandsStaged<K, C, V, U>::run(raw, h.cls, acc, zd, sk);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double r0 = (C == 2) ? __dadd_rn(acc[u][0][0], acc[u][0][C - 1]) : acc[u][0][0];
+            const double r1 = (C == 2) ? __dadd_rn(acc[u][1][0], acc[u][1][C - 1]) : acc[u][1][0];
             double *o = h.out + (ohi + olo[u]);
-            zacc = __dadd_rn(zacc, __dadd_rn(r[0], r[1]));
-            if (h.out_vec) *reinterpret_cast<double2 *>(o) = make_double2(r[0], r[1]);
-            else { o[0] = r[0]; o[h.sol] = r[1]; }
+            zacc = __dadd_rn(zacc, __dadd_rn(r0, r1));
+            if (h.out_vec) *reinterpret_cast<double2 *>(o) = make_double2(r0, r1);
+            else { o[0] = r0; o[h.sol] = r1; }
         }
         __syncthreads();
     }

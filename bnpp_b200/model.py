@@ -169,6 +169,7 @@ class BN:
         self.cards = [int(c) for c in cards]
         self.scopes = [[int(v) for v in sc] for sc, _ in factors]
         sizes = [int(np.asarray(v).size) for _, v in factors]
+        self._sizes, self._offs = sizes, None
         # one pinned staging buffer, one H2D copy, tables 32-byte aligned inside one allocation
         offs, total = [], 0
         for n in sizes:
@@ -179,6 +180,7 @@ class BN:
         hv = self._host.numpy()
         for (sc, v), o, n in zip(factors, offs, sizes):
             hv[o:o + n] = np.asarray(v, dtype=np.float64).reshape(-1)
+        self._offs = offs
         self.h2d_bytes = 8 * total
         with torch.cuda.stream(ctx.torch_stream):
             self._dev = torch.empty(max(1, total), dtype=torch.float64, device="cuda:%d" % ctx.device)
@@ -288,11 +290,7 @@ class BN:
         """BN::sum_product (code/model.cpp:736-753): evidence is ignored, as in the reference"""
         from .sumproduct import FactorGraph
         hv = self._host.numpy()
-        facs = []
-        for sc, p in zip(self.scopes, self.table_ptrs):
-            o = (p - self._dev.data_ptr()) // 8
-            n = int(np.prod([self.cards[v] for v in sc], dtype=np.uint64)) if sc else 1
-            facs.append((sc, hv[o:o + n]))
+        facs = [(sc, hv[o:o + n]) for sc, o, n in zip(self.scopes, self._offs, self._sizes)]
         fg = FactorGraph(self.ctx, self.cards, facs)
         sweeps = fg.update(max_sweeps, epsilon)
         return fg, sweeps
