@@ -75,6 +75,34 @@ __global__ void __launch_bounds__(kBlock) fill_kernel(double *out, uint64_t n, d
     for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += step) out[i] = value;
 }
 
+// Factor::normalize for many small tables at once (the marginals of every variable, each a
+// slice of one buffer): Z summed in index order like the reference's `partition +=`, then the
+// same true division (code/factor.cpp:244-255).  A one-entry slice is the reference's width-0
+// factor [1] of an observed variable (code/model.cpp:333 on a scalar VE result).
+__global__ void normalize_segments_kernel(double *buf, const uint32_t *__restrict__ off, const uint32_t *__restrict__ size, int n)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    double *p = buf + off[s];
+    const uint32_t m = size[s];
+    if (m == 1) {
+        p[0] = 1.0;
+        return;
+    }
+    double z = 0.0;
+    for (uint32_t i = 0; i < m; ++i) z = __dadd_rn(z, p[i]);
+    for (uint32_t i = 0; i < m; ++i) p[i] = __ddiv_rn(p[i], z);
+}
+
+int normalize_segments(bnpp_ctx *ctx, double *buf, const uint32_t *off_dev, const uint32_t *size_dev, int n)
+{
+    if (n <= 0) return BNPP_OK;
+    normalize_segments_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(buf, off_dev, size_dev, n);
+    BNPP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return BNPP_OK;
+}
+
 static unsigned grid_for(bnpp_ctx *ctx, uint64_t n_items)
 {
     uint64_t b = (n_items + kBlock - 1) / kBlock;

@@ -29,6 +29,7 @@ namespace bnpp {
 int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope, int64_t elim_var, int divide,
              double *out_dev, double *z_dev);
 int fill(bnpp_ctx *ctx, double *out, uint64_t n, double value);
+int normalize_segments(bnpp_ctx *ctx, double *buf, const uint32_t *off_dev, const uint32_t *size_dev, int n);
 
 struct PlanFactor {
     std::vector<uint32_t> var, card;
@@ -42,6 +43,9 @@ struct PlanFactor {
 struct PlanStep {
     std::vector<int> operands;
     int out = -1;                           // PlanFactor index, or -2 = the caller's result buffer
+    std::vector<uint32_t> rvar, rcard;      // out == -2: scope written there ...
+    uint64_t roff = 0;                      // ... at this offset (doubles)
+    bool want_z = false;                    // out == -2: also write the partition (the VE result)
     int64_t elim = -1;
     uint64_t union_entries = 0, bytes = 0;
 };
@@ -72,6 +76,10 @@ struct bnpp_ve_plan {
     std::vector<uint32_t *> offtab_dev;
     bool use_graph = true;
     uint64_t runs = 0;                      // the graph is built on the second run: a one-shot plan never pays for it
+    // all-marginals plan (bucket-tree elimination): per variable the slice of the result buffer
+    bool is_mar = false;
+    std::vector<uint32_t> mar_off, mar_size;
+    uint32_t *mar_off_dev = nullptr, *mar_size_dev = nullptr;
     bool profiling = false;
     std::vector<cudaEvent_t> ev;
     std::vector<float> step_ms;
@@ -91,7 +99,8 @@ uint64_t table_size(const std::vector<uint32_t> &card)
 
 // one fused launch description: product of `ops`, optionally eliminating `elim`, output
 // in canonical order (descending rank => the lowest-rank variable is the fastest axis)
-int add_step(bnpp_ve_plan *pl, std::vector<int> ops, int64_t elim, const std::map<uint32_t, uint64_t> &rank, bool to_result)
+int add_step(bnpp_ve_plan *pl, std::vector<int> ops, int64_t elim, const std::map<uint32_t, uint64_t> &rank, bool to_result,
+             uint64_t roff = 0, bool want_z = true)
 {
     std::vector<std::pair<uint64_t, std::pair<uint32_t, uint32_t>>> u;   // (rank, (var, card))
     for (int id : ops) {
@@ -122,6 +131,10 @@ int add_step(bnpp_ve_plan *pl, std::vector<int> ops, int64_t elim, const std::ma
     for (int id : ops) pl->f[id].last_use = step_index;
     if (to_result) {
         st.out = -2;
+        st.rvar = out.var;
+        st.rcard = out.card;
+        st.roff = roff;
+        st.want_z = want_z;
         pl->result_var = out.var;
         pl->result_card = out.card;
         pl->result_size = out.size;
@@ -199,6 +212,62 @@ void shrink(bnpp_ve_plan *pl, std::vector<int> &ops, const std::map<uint32_t, ui
     }
 }
 
+// the input tables as evidence-reduced views (code/domain.cpp:74-90: free axes keep their order)
+int add_inputs(bnpp_ve_plan *pl, int nfac, const bnpp_scope *scopes, const std::map<uint32_t, int> &obs_index,
+               std::map<uint32_t, uint64_t> &rank)
+{
+    for (int q = 0; q < nfac; ++q) {
+        const bnpp_scope &s = scopes[q];
+        if (s.rank < 0 || s.rank > BNPP_MAX_RANK) return BNPP_EINVAL;
+        PlanFactor pf;
+        pf.src = q;
+        uint64_t dense = 1;
+        std::vector<int64_t> st(s.rank);
+        for (int i = s.rank - 1; i >= 0; --i) {
+            st[i] = (int64_t)dense;
+            dense *= s.card[i];
+        }
+        for (int i = 0; i < s.rank; ++i) {
+            auto o = obs_index.find(s.var_id[i]);
+            if (o != obs_index.end()) {
+                pf.obs.push_back({st[i], o->second});
+                continue;
+            }
+            pf.var.push_back(s.var_id[i]);
+            pf.card.push_back(s.card[i]);
+            pf.stride.push_back(st[i]);
+            if (!rank.count(s.var_id[i])) rank[s.var_id[i]] = (1ull << 40) + (0xffffffffull - s.var_id[i]);   // kept: ascending id, most significant first
+        }
+        pf.size = table_size(pf.card);
+        pl->f.push_back(pf);
+    }
+    return BNPP_OK;
+}
+
+// product of `ops`, then every variable outside `keep` summed out one fused launch at a time
+// (the first launch also does the product); -1 when there is nothing to multiply
+int chain(bnpp_ve_plan *pl, std::vector<int> ops, const std::vector<uint32_t> &keep, const std::map<uint32_t, uint64_t> &rank,
+          bool to_result, uint64_t roff)
+{
+    if (ops.empty()) return -1;
+    std::vector<std::pair<uint64_t, uint32_t>> gone;   // (rank, var) of the variables to eliminate
+    for (int id : ops)
+        for (uint32_t v : pl->f[id].var) {
+            bool kept = std::find(keep.begin(), keep.end(), v) != keep.end(), seen = false;
+            for (auto &g : gone) seen |= (g.second == v);
+            if (!kept && !seen) gone.push_back({rank.at(v), v});
+        }
+    std::sort(gone.begin(), gone.end());
+    shrink(pl, ops, rank);
+    if (gone.empty()) return add_step(pl, ops, -1, rank, to_result, roff, false);
+    int t = -1;
+    for (size_t i = 0; i < gone.size(); ++i) {
+        const bool last = (i + 1 == gone.size());
+        t = add_step(pl, i == 0 ? ops : std::vector<int>{t}, (int64_t)gone[i].second, rank, to_result && last, roff, false);
+    }
+    return t;
+}
+
 // Arena layout (first-fit over the step sequence, 256-byte granules) and one resolved launch per
 // step.  Descriptors are planned against stand-in pointers that carry only the ALIGNMENT the
 // real ones are guaranteed to have: intermediates sit on 256-byte boundaries of the arena;
@@ -271,9 +340,9 @@ void build_exec(bnpp_ve_plan *pl)
         bnpp_scope os;
         double *dst;
         if (st.out == -2) {
-            os.rank = (int32_t)pl->result_var.size();
-            os.var_id = pl->result_var.data();
-            os.card = pl->result_card.data();
+            os.rank = (int32_t)st.rvar.size();
+            os.var_id = st.rvar.data();
+            os.card = st.rcard.data();
             dst = result_standin;
         } else {
             const PlanFactor &of = pl->f[st.out];
@@ -311,34 +380,9 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
         rank[order[i]] = (uint64_t)i;
     }
 
-    // inputs as evidence-reduced views (code/domain.cpp:74-90: free axes keep their order)
-    for (int q = 0; q < nfac; ++q) {
-        const bnpp_scope &s = scopes[q];
-        if (s.rank < 0 || s.rank > BNPP_MAX_RANK) {
-            delete pl;
-            return fail(ctx, BNPP_EINVAL, "bad factor scope");
-        }
-        PlanFactor pf;
-        pf.src = q;
-        uint64_t dense = 1;
-        std::vector<int64_t> st(s.rank);
-        for (int i = s.rank - 1; i >= 0; --i) {
-            st[i] = (int64_t)dense;
-            dense *= s.card[i];
-        }
-        for (int i = 0; i < s.rank; ++i) {
-            auto o = obs_index.find(s.var_id[i]);
-            if (o != obs_index.end()) {
-                pf.obs.push_back({st[i], o->second});
-                continue;
-            }
-            pf.var.push_back(s.var_id[i]);
-            pf.card.push_back(s.card[i]);
-            pf.stride.push_back(st[i]);
-            if (!rank.count(s.var_id[i])) rank[s.var_id[i]] = (1ull << 40) + (0xffffffffull - s.var_id[i]);   // kept: ascending id, most significant first
-        }
-        pf.size = table_size(pf.card);
-        pl->f.push_back(pf);
+    if (int rc = add_inputs(pl, nfac, scopes, obs_index, rank)) {
+        delete pl;
+        return fail(ctx, rc, "bad factor scope");
     }
 
     // bucket = factors whose earliest-eliminated variable is order[i] (code/model.cpp:390-406)
@@ -386,6 +430,145 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
     return BNPP_OK;
 }
 
+// All marginals in ONE plan: bucket-tree elimination (two passes over the bucket tree of the
+// order) instead of the reference's N complete VE passes (code/model.cpp:326-334; SURVEY §8f
+// row 2).  Upward pass = variable elimination, every bucket sends lambda to its parent
+// bucket; downward pass, every bucket sends each child the product of everything else it
+// holds, summed down to that child's separator.  The marginal of v is the product of all
+// functions and messages in bucket v summed over the rest of its clique, normalised --
+// mathematically the table the reference's pass for v produces (agreement ~1e-15).
+// result layout: per variable id ascending, card(v) doubles, or ONE double (= 1) for an
+// observed variable or one that no factor mentions (the reference's width-0 factor [1]).
+int bnpp_mar_plan_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_obs,
+                         const uint32_t *obs_var, int n_order, const uint32_t *order, bnpp_ve_plan **out)
+{
+    if (!ctx || !out || nvars < 0 || nfac < 0 || n_obs < 0 || n_order < 0) return BNPP_EINVAL;
+    *out = nullptr;
+    bnpp_ve_plan *pl = new bnpp_ve_plan();
+    pl->ctx = ctx;
+    pl->n_inputs = nfac;
+    pl->is_mar = true;
+    std::map<uint32_t, int> obs_index;
+    for (int i = 0; i < n_obs; ++i) obs_index[obs_var[i]] = i;
+    std::map<uint32_t, uint64_t> rank;
+    for (int i = 0; i < n_order; ++i) {
+        if (rank.count(order[i]) || obs_index.count(order[i])) {
+            delete pl;
+            return fail(ctx, BNPP_EINVAL, "elimination order repeats a variable or names an observed one");
+        }
+        rank[order[i]] = (uint64_t)i;
+    }
+    if (int rc = add_inputs(pl, nfac, scopes, obs_index, rank)) {
+        delete pl;
+        return fail(ctx, rc, "bad factor scope");
+    }
+    for (const PlanFactor &pf : pl->f)
+        for (uint32_t v : pf.var)
+            if (rank.at(v) >= (uint64_t)n_order) {
+                delete pl;
+                return fail(ctx, BNPP_EINVAL, "marginals plan: the order must cover every unobserved variable of the factors");
+            }
+
+    // result slices
+    std::vector<char> mentioned(nvars, 0);
+    for (const PlanFactor &pf : pl->f)
+        for (uint32_t v : pf.var)
+            if (v < (uint32_t)nvars) mentioned[v] = 1;
+    pl->mar_off.assign(nvars, 0);
+    pl->mar_size.assign(nvars, 1);
+    uint32_t total = 0;
+    for (int v = 0; v < nvars; ++v) {
+        pl->mar_off[v] = total;
+        pl->mar_size[v] = mentioned[v] ? card[v] : 1;
+        total += pl->mar_size[v];
+    }
+    pl->result_size = total;
+
+    struct Bucket {
+        std::vector<int> funcs;            // original views and lambdas of the children
+        std::vector<int> child_of;         // for funcs[j]: the child bucket that sent it, or -1
+        int mu = -1;                       // message from the parent bucket
+    };
+    std::vector<Bucket> B(n_order);
+    auto place = [&](int id, int from) {
+        uint64_t best = UINT64_MAX;
+        for (uint32_t v : pl->f[id].var) best = std::min(best, rank.at(v));
+        if (best < (uint64_t)n_order) {
+            B[best].funcs.push_back(id);
+            B[best].child_of.push_back(from);
+        }
+    };
+    for (int q = 0; q < nfac; ++q) place(q, -1);
+    // upward: lambda_i = sum over order[i] of everything in bucket i
+    for (int i = 0; i < n_order; ++i) {
+        if (B[i].funcs.empty()) continue;
+        std::vector<int> ops = B[i].funcs;
+        shrink(pl, ops, rank);
+        const int lam = add_step(pl, ops, (int64_t)order[i], rank, false);
+        pl->union_entries += pl->steps.back().union_entries;
+        pl->max_step_entries = std::max(pl->max_step_entries, pl->steps.back().union_entries);
+        place(lam, i);
+    }
+    // downward
+    for (int i = n_order - 1; i >= 0; --i) {
+        Bucket &b = B[i];
+        if (b.funcs.empty()) continue;
+        std::vector<int> G = b.funcs;
+        if (b.mu >= 0) G.push_back(b.mu);
+        const uint32_t v = order[i];
+        if (v < (uint32_t)nvars) chain(pl, G, std::vector<uint32_t>{v}, rank, true, pl->mar_off[v]);
+        for (size_t j = 0; j < b.funcs.size(); ++j) {
+            const int c = b.child_of[j];
+            if (c < 0) continue;
+            std::vector<int> Gc;
+            for (size_t t = 0; t < G.size(); ++t)
+                if (t != j) Gc.push_back(G[t]);
+            B[c].mu = chain(pl, Gc, pl->f[b.funcs[j]].var, rank, false, 0);
+        }
+    }
+    pl->result_var.clear();
+    pl->result_card.clear();
+    pl->result_size = total;
+
+    uint64_t live = 0;
+    for (size_t s = 0; s < pl->steps.size(); ++s) {
+        const PlanStep &st = pl->steps[s];
+        pl->bytes += st.bytes;
+        if (st.out >= 0) live += 8 * pl->f[st.out].size;
+        pl->peak_bytes = std::max(pl->peak_bytes, live);
+        for (int id : st.operands)
+            if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) live -= 8 * pl->f[id].size;
+    }
+    build_exec(pl);
+    double *store = nullptr;
+    int rc = bnpp_alloc(ctx, (uint64_t)nvars + 2, &store);   // 2 * nvars uint32
+    if (rc != BNPP_OK) {
+        delete pl;
+        return rc;
+    }
+    pl->mar_off_dev = reinterpret_cast<uint32_t *>(store);
+    pl->mar_size_dev = pl->mar_off_dev + nvars;
+    if (nvars) {
+        cudaMemcpyAsync(pl->mar_off_dev, pl->mar_off.data(), sizeof(uint32_t) * nvars, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(pl->mar_size_dev, pl->mar_size.data(), sizeof(uint32_t) * nvars, cudaMemcpyHostToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    *out = pl;
+    return BNPP_OK;
+}
+
+// slices of the marginals result: offset and size (doubles) per variable id
+int bnpp_mar_plan_layout(const bnpp_ve_plan *pl, int nvars, uint32_t *off, uint32_t *size, uint64_t *total)
+{
+    if (!pl || !pl->is_mar) return BNPP_EINVAL;
+    for (int v = 0; v < nvars && v < (int)pl->mar_off.size(); ++v) {
+        if (off) off[v] = pl->mar_off[v];
+        if (size) size[v] = pl->mar_size[v];
+    }
+    if (total) *total = pl->result_size;
+    return BNPP_OK;
+}
+
 int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
 {
     if (!pl) return BNPP_OK;
@@ -393,6 +576,7 @@ int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
     if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
     if (pl->graph) cudaGraphDestroy(pl->graph);
     if (pl->arena) bnpp_free(pl->ctx, pl->arena);
+    if (pl->mar_off_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->mar_off_dev));
     for (uint32_t *t : pl->offtab_dev)
         if (t) bnpp_free(pl->ctx, reinterpret_cast<double *>(t));
     delete pl;
@@ -480,10 +664,10 @@ static int run_dynamic(bnpp_ve_plan *pl, const std::vector<const double *> &ptr_
         bnpp_scope os;
         double *dst;
         if (st.out == -2) {
-            os.rank = (int32_t)pl->result_var.size();
-            os.var_id = pl->result_var.data();
-            os.card = pl->result_card.data();
-            dst = result_dev;
+            os.rank = (int32_t)st.rvar.size();
+            os.var_id = st.rvar.data();
+            os.card = st.rcard.data();
+            dst = result_dev + st.roff;
         } else {
             const PlanFactor &of = pl->f[st.out];
             os.rank = (int32_t)of.var.size();
@@ -494,7 +678,7 @@ static int run_dynamic(bnpp_ve_plan *pl, const std::vector<const double *> &ptr_
             dst = owned[st.out];
             ptr[st.out] = dst;
         }
-        rc = contract(ctx, (int)st.operands.size(), ops, &os, st.elim, 0, dst, st.out == -2 ? z_dev : nullptr);
+        rc = contract(ctx, (int)st.operands.size(), ops, &os, st.elim, 0, dst, (st.out == -2 && st.want_z) ? z_dev : nullptr);
         if (pl->profiling) {
             pl->step_kernel.resize(pl->steps.size());
             pl->step_kernel[s] = ctx->last_kernel;
@@ -525,7 +709,7 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
         ptr[i] = tables_dev[pf.src] + base;
         aligned32 = aligned32 && (reinterpret_cast<uintptr_t>(tables_dev[pf.src]) % 32 == 0);
     }
-    if (pl->steps.empty() || pl->steps.back().out != -2) {
+    if (!pl->is_mar && (pl->steps.empty() || pl->steps.back().out != -2)) {
         int rc = fill(ctx, result_dev, 1, 1.0);   // no factor left: the scalar 1 (code/model.cpp:355)
         if (rc != BNPP_OK) return rc;
         if (z_dev) rc = fill(ctx, z_dev, 1, 1.0);
@@ -553,8 +737,8 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             if (pl->profiling) cudaEventRecord(pl->ev[s], ctx->stream);
             const double *in[kMaxK];
             for (size_t q = 0; q < st.operands.size(); ++q) in[q] = ptr[st.operands[q]];
-            double *dst = st.out == -2 ? result_dev : pl->arena + pl->arena_off[st.out];
-            double *z = st.out == -2 ? z_dev : nullptr;
+            double *dst = st.out == -2 ? result_dev + st.roff : pl->arena + pl->arena_off[st.out];
+            double *z = (st.out == -2 && st.want_z) ? z_dev : nullptr;
             if (!(graphed && pl->use_graph)) {
                 rc = contract_launch(ctx, pl->exec[s], in, dst, z);
                 continue;
@@ -591,6 +775,8 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             for (size_t s = 0; s < pl->steps.size(); ++s) pl->step_kernel[s] = pl->exec[s].name;
         }
     }
+    if (rc == BNPP_OK && pl->is_mar)
+        rc = normalize_segments(ctx, result_dev, pl->mar_off_dev, pl->mar_size_dev, (int)pl->mar_off.size());
     if (pl->profiling) cudaEventRecord(pl->ev[pl->steps.size()], ctx->stream);
     pl->runs++;
     return rc;
@@ -643,8 +829,8 @@ int bnpp_ve_plan_run_batched(bnpp_ve_plan *pl, const double *const *tables_dev, 
             double *dst;
             const std::vector<uint32_t> *ov, *oc;
             if (st.out == -2) {
-                ov = &pl->result_var;
-                oc = &pl->result_card;
+                ov = &st.rvar;
+                oc = &st.rcard;
                 dst = result_dev + b0;   // result_size == 1 when slicing
             } else {
                 const PlanFactor &of = pl->f[st.out];

@@ -161,16 +161,83 @@ double Model::partition_ve(const std::unordered_map<unsigned,unsigned> &evidence
     return part.partition();
 }
 
+// BN::marginals, VE branch (code/model.cpp:320-339).  The reference runs one complete VE pass per
+// variable; here all marginals come from ONE two-pass bucket-tree plan on the device
+// (bnpp_mar_plan_create) -- the same tables up to rounding.  With -v and an ordering flag the
+// reference prints the order of every pass, so that combination keeps the pass-per-variable form.
 std::vector<const Factor*> Model::marginals_ve(const std::unordered_map<unsigned,unsigned> &evidence,
                                                std::unordered_map<std::string,bool> &options) const
 {
     std::vector<const Factor*> factors(_factors.begin(), _factors.end());
     std::vector<const Factor*> marg;
-    for (const Variable *pv : _variables) {
-        std::vector<const Variable*> vars;
-        for (const Variable *pv2 : _variables)
-            if (pv2 != pv) vars.push_back(pv2);
-        marg.push_back(new Factor(eliminate(vars, factors, evidence, options).normalize()));
+    const bool heuristic = options["min-fill"] || options["weighted-min-fill"] || options["min-degree"];
+    if (options["verbose"] && heuristic) {
+        for (const Variable *pv : _variables) {
+            std::vector<const Variable*> vars;
+            for (const Variable *pv2 : _variables)
+                if (pv2 != pv) vars.push_back(pv2);
+            marg.push_back(new Factor(eliminate(vars, factors, evidence, options).normalize()));
+        }
+        return marg;
+    }
+
+    std::vector<unsigned> ids;
+    for (const Variable *pv : _variables)
+        if (evidence.find(pv->id()) == evidence.end()) ids.push_back(pv->id());
+    std::vector<unsigned> card;
+    for (const Variable *pv : _variables) card.push_back(pv->size());
+    if (heuristic) {
+        std::vector<std::vector<unsigned>> scopes;
+        for (const Factor *pf : factors) {
+            std::vector<unsigned> sc;
+            for (uint32_t id : pf->domain().ids())
+                if (evidence.find(id) == evidence.end()) sc.push_back(id);
+            scopes.push_back(sc);
+        }
+        bnpp::InteractionGraph g(scopes, card);
+        bnpp::Heuristic h = bnpp::H_MIN_FILL;
+        if (options["min-degree"]) h = bnpp::H_MIN_DEGREE;
+        else if (options["weighted-min-fill"]) h = bnpp::H_WEIGHTED_MIN_FILL;
+        unsigned width = 0;
+        ids = bnpp::FastOrderer(g).ordering(ids, h, width);
+    }
+    std::vector<bnpp_scope> scopes(factors.size());
+    std::vector<const double*> tables(factors.size());
+    for (size_t i = 0; i < factors.size(); ++i) {
+        const Domain &d = factors[i]->domain();
+        scopes[i].rank = (int32_t)d.width();
+        scopes[i].var_id = d.ids().data();
+        scopes[i].card = d.cards().data();
+        tables[i] = factors[i]->device_data();
+    }
+    std::vector<uint32_t> obs_var, obs_val;
+    for (const auto &e : evidence) {
+        obs_var.push_back(e.first);
+        obs_val.push_back(e.second);
+    }
+    bnpp_ctx *ctx = gpu::ctx();
+    bnpp_ve_plan *plan = nullptr;
+    const int nvars = (int)_variables.size();
+    gpu::check(bnpp_mar_plan_create(ctx, nvars, card.data(), (int)factors.size(), scopes.data(), (int)obs_var.size(),
+                                    obs_var.data(), (int)ids.size(), ids.data(), &plan), "bnpp_mar_plan_create");
+    std::vector<uint32_t> off(nvars), size(nvars);
+    uint64_t total = 0;
+    gpu::check(bnpp_mar_plan_layout(plan, nvars, off.data(), size.data(), &total), "bnpp_mar_plan_layout");
+    double *res = nullptr;
+    gpu::check(bnpp_alloc(ctx, total + 1, &res), "bnpp_alloc");
+    gpu::check(bnpp_ve_plan_run(plan, tables.data(), obs_val.data(), res, nullptr), "bnpp_ve_plan_run");
+    std::vector<double> host(total + 1);
+    gpu::check(bnpp_download(ctx, host.data(), res, total), "bnpp_download");
+    bnpp_free(ctx, res);
+    bnpp_ve_plan_destroy(plan);
+    for (int v = 0; v < nvars; ++v) {
+        if (size[v] == 1 && _variables[v]->size() != 1) {
+            marg.push_back(new Factor(1.0));      // observed (or unmentioned) variable: the width-0 factor [1]
+            continue;
+        }
+        std::vector<const Variable*> sc(1, _variables[v]);
+        std::vector<double> values(host.begin() + off[v], host.begin() + off[v] + size[v]);
+        marg.push_back(new Factor(new Domain(sc), values, 1.0));
     }
     return marg;
 }

@@ -170,6 +170,16 @@ int bnpp_ve_plan_info(const bnpp_ve_plan *plan, int32_t *result_rank, uint32_t *
  * buffer of the result's size; z_dev: optional device double for its partition.  Asynchronous. */
 int bnpp_ve_plan_run(bnpp_ve_plan *plan, const double *const *tables_dev, const uint32_t *obs_val,
                      double *result_dev, double *z_dev);
+/* BN::marginals (code/model.cpp:320-339) for EVERY variable in one plan: two passes over the
+ * bucket tree of `order` (which must cover all unobserved variables) instead of one VE pass
+ * per variable.  Run it with bnpp_ve_plan_run: result_dev receives, per variable id
+ * ascending, card(v) normalised doubles -- or a single 1.0 for an observed variable or one no
+ * factor mentions (the reference returns the width-0 factor [1] there).  bnpp_mar_plan_layout
+ * gives each variable's offset and size and the total. */
+int bnpp_mar_plan_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_obs,
+                         const uint32_t *obs_var, int n_order, const uint32_t *order, bnpp_ve_plan **out);
+int bnpp_mar_plan_layout(const bnpp_ve_plan *plan, int nvars, uint32_t *off, uint32_t *size, uint64_t *total);
+
 /* K8 -- the same plan for a BATCH of evidence sets (BASELINE config 5): ev_dev is a device
  * matrix [nb][n_obs] of evidence values (uint8, column j = obs_var[j] of the plan);
  * result_dev receives [result_size][nb] doubles, batch fastest (PR: one double per set).

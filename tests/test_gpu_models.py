@@ -173,3 +173,39 @@ def test_evidence_batch_large(ctx):
         assert zi == z[i]
     assert np.all(z > 0) and np.all(z < 1)
     bn.close()
+
+
+def test_marginals_bucket_tree(ctx, golden_models, golden_synth):
+    """all marginals from one two-pass bucket-tree plan == the reference's N VE passes (1e-9),
+    with and without evidence, several orderings, binary and multi-valued networks"""
+    n = 0
+    for name in ["asia", "asia_positive", "cancer", "earthquake", "child", "alarm", "grid3x3", "network"]:
+        m = golden_models[name]
+        bn = load(ctx, m["uai"])
+        for case in m["mar"]:
+            ev = {int(k): v for k, v in case["evidence"].items()}
+            for h in ("mf", "md", "wmf", None):
+                got = bn.marginals_fast(ev, h)
+                for v, (g, want) in enumerate(zip(got, case["mar"])):
+                    assert len(g) == len(want), (name, v)
+                    assert np.allclose(g, want, rtol=REL, atol=1e-300), (name, h, v, g, want)
+                n += 1
+        bn.close()
+    assert n >= 40
+    # exact marginals of the 4x4 Ising grid (loopy graph, treewidth 4)
+    rec = [r for r in golden_synth["ising"] if r["n"] == 4][0]
+    bn = load(ctx, synth.ising_uai(4, rec["h"], rec["J"], rec["seed"]))
+    got = bn.marginals_fast({}, "mf")
+    assert np.allclose([g[0] for g in got], rec["exact_p0"], rtol=REL, atol=0.0)
+    bn.close()
+
+
+def test_marginals_bucket_tree_vs_passes_wide(ctx):
+    """a width-15 network: the two-pass plan against one VE pass per variable (both on the device)"""
+    bn = load(ctx, synth.random_bn_uai(40, 24, 3, 3))
+    ev = {5: 1, 17: 0, 33: 1}
+    fast = bn.marginals_fast(ev, "mf")
+    slow = bn.marginals(ev, "mf")
+    for v, (a, b) in enumerate(zip(fast, slow)):
+        assert np.allclose(a, b, rtol=REL, atol=1e-300), v
+    bn.close()

@@ -34,6 +34,13 @@ ms, (z, _) = timed(lambda: asia.partition(ev, "mf"))
 out["asia_pr_mf"] = {"ms": ms, "queries_per_s": 1e3 / ms, "Z": z}
 ms, mar = timed(lambda: asia.marginals(ev, None), 20)
 out["asia_mar"] = {"ms": ms, "P(x7=0|e)": float(mar[7][0])}
+ms, mar = timed(lambda: asia.marginals_fast(ev, "mf"), 20)
+out["asia_mar_bucket_tree"] = {"ms": ms, "P(x7=0|e)": float(mar[7][0])}
+_, net = model.from_uai_text(ctx, G["network"]["uai"])
+ms, mar = timed(lambda: net.marginals({}, "mf"), 2)
+out["network120_mar_passes_mf"] = {"ms": ms, "P(x0=0)": float(mar[0][0])}
+ms, mar = timed(lambda: net.marginals_fast({}, "mf"), 10)
+out["network120_mar_bucket_tree_mf"] = {"ms": ms, "P(x0=0)": float(mar[0][0])}
 _, grid = model.from_uai_text(ctx, G["grid3x3"]["uai"])
 ms, (z, _) = timed(lambda: grid.partition({0: 1, 4: 1, 5: 1}, "mf"))
 out["grid3x3_pr_mf"] = {"ms": ms, "Z": z}
