@@ -224,3 +224,58 @@ def test_sum_out_commutes_and_partition_invariant_2p26(ctx):
     s1 = a.sum_out(3).sum_out(20)
     s2 = a.sum_out(20).sum_out(3)
     assert torch.allclose(s1.buf[:-1], s2.buf[:-1], rtol=1e-14, atol=0.0)   # (p+q)+(r+s) vs (p+r)+(q+s)
+
+
+def test_transposed_operands_through_shared_memory(ctx):
+    """operands whose fastest axes are the output's slowest go through the shared-memory tile
+    (`staged` variant): pure products and fused steps, K = 1..3, entry-wise against the oracle"""
+    from bnpp_b200.factor import fused_product_sum_out
+    rng = random.Random(21)
+    nbits = 18
+    cards = [2] * nbits
+    allv = list(range(nbits))
+    seen = set()
+    cases = [
+        ([allv[::-1]], None),                                   # K=1: a full bit-reversal copy
+        ([allv, allv[::-1]], None),                             # product, B reversed
+        ([allv, allv[::-1]], 7),                                # fused, B reversed
+        ([allv[:-1], allv[::-1], [3, 9]], 17),                  # K=3, the big reversed one in the middle
+        ([allv[::-1], allv[2:]], 0),                            # the reversed operand first
+    ]
+    for scopes, elim in cases:
+        ofs, dfs = [], []
+        for sc in scopes:
+            o, d = rand_factor(ctx, rng, sc, cards)
+            ofs.append(o); dfs.append(d)
+        out_scope = [v for v in allv if v != elim]
+        want = orc.product_sum_out(ofs, out_scope, elim, cards)
+        got = fused_product_sum_out(ctx, dfs, out_scope, elim)
+        seen.add(ctx.last_launch()[0].split(",")[0])
+        assert np.array_equal(got.values(), want.values), (scopes, elim, ctx.last_launch())
+        assert zclose(got.partition, want.partition)
+    assert any("staged" in s for s in seen), seen
+
+
+def test_bcast_2p30_partition_invariant(ctx):
+    """largest single-GPU shapes: 2^30 union entries (4 GiB operands); Z(sum_out) must not depend on
+    which variable is summed out, and must equal the direct reduction of a product slice"""
+    import torch
+    from bnpp_b200.factor import DeviceFactor, fused_product_sum_out
+    nbits = 30
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = DeviceFactor.empty(ctx, list(range(nbits - 1)), [2] * (nbits - 1))
+    b = DeviceFactor.empty(ctx, list(range(1, nbits)), [2] * (nbits - 1))
+    a.buf[:-1] = torch.rand(a.size, generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+    b.buf[:-1] = torch.rand(b.size, generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+    torch.cuda.synchronize()
+    zs = []
+    for k in (0, 15, 29):
+        out = fused_product_sum_out(ctx, [a, b], [v for v in range(nbits) if v != k], k)
+        zs.append(out.partition)
+        del out
+    assert all(math.isclose(z, zs[0], rel_tol=1e-12) for z in zs)
+    # Z = sum_{x0} sum_{x29} sum_rest A[x0,rest] B[rest,x29] = <sum_x0 A, sum_x29 B>
+    sa = a.buf[:-1].view(2, -1).sum(0)
+    sb = b.buf[:-1].view(-1, 2).sum(1)
+    want = float(torch.dot(sa, sb).item())
+    assert math.isclose(zs[0], want, rel_tol=1e-11)
