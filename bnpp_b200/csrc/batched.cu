@@ -117,6 +117,91 @@ __global__ void __launch_bounds__(kBlock) contract_batched(const __grid_constant
     }
 }
 
+// Binary eliminated variable (every BASELINE network): UO output entries of a thread are
+// processed together -- all their loads are issued before the first multiply, so one wave of
+// CTAs moves UO times the bytes per memory round trip (the launch is a handful of waves long,
+// each paying a full DRAM latency).
+template <int K, int VB, int UO>
+__global__ void __launch_bounds__(kBlock) contract_batched_bin(const __grid_constant__ BParams p)
+{
+    const uint32_t nbv = p.nb / VB;
+    const uint64_t total = (uint64_t)p.n_chunks * nbv;
+    const uint64_t step = (uint64_t)gridDim.x * kBlock;
+    for (uint64_t idx = (uint64_t)blockIdx.x * kBlock + threadIdx.x; idx < total; idx += step) {
+        uint32_t chunk, bv;
+        if (nbv == 1) { chunk = (uint32_t)idx; bv = 0; }
+        else if (total < (1ull << 32)) { chunk = fastdiv((uint32_t)idx, p.nbdiv); bv = (uint32_t)idx - chunk * nbv; }
+        else { chunk = (uint32_t)(idx / nbv); bv = (uint32_t)(idx - (uint64_t)chunk * nbv); }
+        const uint32_t b = bv * VB;
+        const double *base[K][VB];
+        uint64_t xs[K], os[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const BOperand &op = p.op[k];
+            if (op.batched) {
+                base[k][0] = op.ptr + b;
+                if (VB == 2) base[k][VB - 1] = base[k][0] + 1;
+                xs[k] = (uint64_t)op.sx * p.nb;
+                os[k] = p.nb;
+            } else {
+                uint32_t e[VB];
+#pragma unroll
+                for (int v = 0; v < VB; ++v) e[v] = 0;
+                for (uint32_t j = 0; j < op.nobs; ++j) {
+                    const uint8_t *col = p.ev + (uint64_t)op.oidx[j] * p.ev_stride + b;
+#pragma unroll
+                    for (int v = 0; v < VB; ++v) e[v] += op.ostride[j] * col[v];
+                }
+#pragma unroll
+                for (int v = 0; v < VB; ++v) base[k][v] = op.ptr + e[v];
+                xs[k] = op.sx;
+                os[k] = 1;
+            }
+        }
+        const uint32_t o_end = min(p.n_out, (chunk + 1) * p.oc);
+        for (uint32_t o0 = chunk * p.oc; o0 < o_end; o0 += UO) {
+            double t[UO][K][2][VB];
+#pragma unroll
+            for (int i = 0; i < UO; ++i) {
+                const uint32_t o = min(o0 + i, o_end - 1);      // tail entries repeat the last one, their result is dropped
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint64_t off = (uint64_t)__ldg(p.offtab + (uint64_t)k * p.n_out + o) * os[k];
+#pragma unroll
+                    for (int x = 0; x < 2; ++x) {
+                        if (VB == 2 && p.op[k].batched) {
+                            const double2 d2 = ld2(base[k][0] + off + x * xs[k]);
+                            t[i][k][x][0] = d2.x;
+                            t[i][k][x][VB - 1] = d2.y;
+                        } else {
+#pragma unroll
+                            for (int w = 0; w < VB; ++w) t[i][k][x][w] = ld1(base[k][w] + off + x * xs[k]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < UO; ++i) {
+                if (o0 + i >= o_end) break;
+                double acc[VB];
+#pragma unroll
+                for (int w = 0; w < VB; ++w) {
+                    double v0 = t[i][0][0][w], v1 = t[i][0][1][w];
+#pragma unroll
+                    for (int k = 1; k < K; ++k) {
+                        v0 = __dmul_rn(v0, t[i][k][0][w]);
+                        v1 = __dmul_rn(v1, t[i][k][1][w]);
+                    }
+                    acc[w] = __dadd_rn(v0, v1);
+                }
+                double *dst = p.out + ((uint64_t)(o0 + i) * p.nb + b);
+                if (VB == 2) *reinterpret_cast<double2 *>(dst) = make_double2(acc[0], acc[VB - 1]);
+                else dst[0] = acc[0];
+            }
+        }
+    }
+}
+
 // [nb][n_obs] (one row per evidence set, as the caller has it) -> [n_obs][nb]
 __global__ void transpose_evidence(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint32_t nb, uint32_t n_obs)
 {
@@ -140,6 +225,18 @@ int transpose_evidence_launch(bnpp_ctx *ctx, const uint8_t *in, uint8_t *out, ui
 }
 
 typedef void (*batched_fn)(const BParams);
+
+template <int VB>
+static batched_fn pick_batched_bin(int K, int &uo)
+{
+    switch (K) {
+    case 1: uo = 4; return contract_batched_bin<1, VB, 4>;
+    case 2: uo = 4; return contract_batched_bin<2, VB, 4>;
+    case 3: uo = 2; return contract_batched_bin<3, VB, 2>;
+    case 4: uo = 2; return contract_batched_bin<4, VB, 2>;
+    default: uo = 0; return nullptr;
+    }
+}
 
 template <int VB>
 static batched_fn pick_batched_v(int K)
@@ -229,25 +326,31 @@ int contract_batched_step(bnpp_ctx *ctx, int k, const BatchedOperandDesc *ops, c
     p.ev_stride = ev_stride;
     p.n_obs = n_obs;
     p.nb = nb;
+    p.n_out = (uint32_t)n_out;
+    p.cx = cx;
     // two sets per thread when every batched table keeps 16-byte alignment: even slice, aligned bases
     int vb = (nb % 2 == 0 && reinterpret_cast<uintptr_t>(out_dev) % 16 == 0) ? 2 : 1;
     for (int q = 0; q < k && vb == 2; ++q)
         if (ops[q].batched && reinterpret_cast<uintptr_t>(ops[q].ptr) % 16 != 0) vb = 1;
     p.nbdiv = make_fastdiv(nb / vb > 1 ? nb / vb : 2);
-    // enough threads to fill the machine, as many output entries per thread as that leaves
-    const uint64_t want_threads = (uint64_t)ctx->sm_count * 2048;
-    uint64_t oc = (n_out * (nb / vb)) / want_threads;
+    // binary eliminated variable with at most 4 operands: the unrolled variant
+    int uo = 0;
+    batched_fn fn = nullptr;
+    if (cx == 2) fn = (vb == 2) ? pick_batched_bin<2>(k, uo) : pick_batched_bin<1>(k, uo);
+    if (!fn) fn = (vb == 2) ? pick_batched_v<2>(k) : pick_batched_v<1>(k);
+    // about one resident wave of threads, each walking `oc` consecutive output entries
+    const uint64_t want_threads = (uint64_t)ctx->sm_count * (uo ? 768 : 2048);
+    uint64_t oc = (n_out * (nb / vb) + want_threads - 1) / want_threads;
     if (oc < 1) oc = 1;
-    if (oc > 16) oc = 16;
+    if (uo && oc < (uint64_t)uo && n_out >= (uint64_t)uo) oc = uo;
+    if (oc > 32) oc = 32;
     p.oc = (uint32_t)oc;
     p.n_chunks = (uint32_t)((n_out + oc - 1) / oc);
-    p.n_out = (uint32_t)n_out;
-    p.cx = cx;
     const uint64_t total = (uint64_t)p.n_chunks * (nb / vb);
     uint64_t blocks = (total + kBlock - 1) / kBlock;
     const uint64_t cap = (uint64_t)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
-    (vb == 2 ? pick_batched_v<2>(k) : pick_batched_v<1>(k))<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(p);
+    fn<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(p);
     BNPP_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return BNPP_OK;
