@@ -74,6 +74,10 @@ struct bnpp_ve_plan {
     // batched replay: per-step operand-offset tables (host copy + device copy, built on first use)
     std::vector<std::vector<uint32_t>> offtab_host;
     std::vector<uint32_t *> offtab_dev;
+    // batched replay as a captured graph (allocations included), valid while the caller's buffers stay put
+    cudaGraphExec_t batch_exec = nullptr;
+    std::vector<const void *> batch_key;
+    uint64_t batch_runs = 0;
     bool use_graph = true;
     uint64_t runs = 0;                      // the graph is built on the second run: a one-shot plan never pays for it
     // all-marginals plan (bucket-tree elimination): per variable the slice of the result buffer
@@ -573,6 +577,10 @@ int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
 {
     if (!pl) return BNPP_OK;
     for (cudaEvent_t e : pl->ev) cudaEventDestroy(e);
+    if (pl->batch_exec) {
+        cudaGraphExecDestroy(pl->batch_exec);
+        cudaDeviceGraphMemTrim(pl->ctx->device);   // hand the graph's allocations back
+    }
     if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
     if (pl->graph) cudaGraphDestroy(pl->graph);
     if (pl->arena) bnpp_free(pl->ctx, pl->arena);
@@ -786,10 +794,61 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
 // ids are the plan's, ev_dev[b][j] is the value of obs_var[j] in set b.  result_dev receives
 // [result_size][nb] (batch fastest).  Sets are processed in slices that keep the widest
 // intermediate below ~1 GiB.
+static int run_batched_once(bnpp_ve_plan *pl, const double *const *tables_dev, uint32_t nb, uint32_t n_obs,
+                            const uint8_t *ev_dev, double *result_dev);
+
+// The launches of a batched run are tiny when the batch is sharded over many GPUs, so from the
+// third run with the same buffers on, the whole run (stream-ordered allocations included) is
+// replayed as one captured CUDA graph.
 int bnpp_ve_plan_run_batched(bnpp_ve_plan *pl, const double *const *tables_dev, uint32_t nb, uint32_t n_obs,
                              const uint8_t *ev_dev, double *result_dev)
 {
     if (!pl || !result_dev || nb == 0) return BNPP_EINVAL;
+    bnpp_ctx *ctx = pl->ctx;
+    std::vector<const void *> key;
+    key.push_back(ev_dev);
+    key.push_back(result_dev);
+    key.push_back(reinterpret_cast<const void *>(static_cast<uintptr_t>(nb)));
+    for (int q = 0; q < pl->n_inputs; ++q) key.push_back(tables_dev[q]);
+    if (pl->batch_exec && key == pl->batch_key) {
+        BNPP_CUDA(ctx, cudaGraphLaunch(pl->batch_exec, ctx->stream));
+        ctx->launches += pl->steps.size() + 1;
+        return BNPP_OK;
+    }
+    if (pl->batch_exec) {
+        cudaGraphExecDestroy(pl->batch_exec);
+        pl->batch_exec = nullptr;
+        pl->batch_runs = 0;
+    }
+    // run 0 is plain (it uploads the offset tables from pageable memory, which a capture must not
+    // contain); run 1 with the same buffers is captured and launched
+    if (pl->use_graph && pl->batch_runs >= 1 && key == pl->batch_key) {
+        cudaGraph_t g = nullptr;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const uint64_t before = ctx->launches;
+            const int rc = run_batched_once(pl, tables_dev, nb, n_obs, ev_dev, result_dev);
+            const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+            ctx->launches = before;
+            if (rc == BNPP_OK && e == cudaSuccess && cudaGraphInstantiate(&pl->batch_exec, g, 0) == cudaSuccess) {
+                cudaGraphDestroy(g);
+                BNPP_CUDA(ctx, cudaGraphLaunch(pl->batch_exec, ctx->stream));
+                ctx->launches += pl->steps.size() + 1;
+                return BNPP_OK;
+            }
+            if (g) cudaGraphDestroy(g);
+            cudaGetLastError();
+            pl->batch_exec = nullptr;
+            pl->use_graph = false;      // capture not possible here: stay on plain launches
+        }
+    }
+    pl->batch_key = key;
+    pl->batch_runs++;
+    return run_batched_once(pl, tables_dev, nb, n_obs, ev_dev, result_dev);
+}
+
+static int run_batched_once(bnpp_ve_plan *pl, const double *const *tables_dev, uint32_t nb, uint32_t n_obs,
+                            const uint8_t *ev_dev, double *result_dev)
+{
     bnpp_ctx *ctx = pl->ctx;
     uint64_t widest = 1;
     for (const PlanFactor &pf : pl->f)

@@ -217,6 +217,7 @@ class BN:
         self.table_ptrs = [self._dev.data_ptr() + 8 * o for o in offs]
         self._plans = {}
         self._res2 = None
+        self._batch_out = {}
         self.last_timing = {}
         self._scope_arr, self._scope_keep = _scopes(self.scopes, self.cards)   # the model's structure never changes
 
@@ -293,7 +294,10 @@ class BN:
             if host_values is not None:
                 values = host_values.to(self._dev.device, non_blocking=True)
             nb = values.shape[0]
-            out = torch.empty(nb, dtype=torch.float64, device=self._dev.device)
+            # one result buffer per batch size, reused: stable pointers let the library replay the run as a graph
+            out = self._batch_out.get(nb)
+            if out is None:
+                out = self._batch_out[nb] = torch.empty(nb, dtype=torch.float64, device=self._dev.device)
         p.run_batched(self.table_ptrs, nb, values.data_ptr(), out.data_ptr())
         self._keep_alive = values
         return out
