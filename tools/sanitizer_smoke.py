@@ -1,6 +1,6 @@
 # small end-to-end exercise for compute-sanitizer: every kernel family once, small sizes
 import sys, gzip, json
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/oracle')
+sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 from bnpp_b200 import capi, model, synth
 from bnpp_b200.factor import DeviceFactor, fused_product_sum_out
