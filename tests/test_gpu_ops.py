@@ -279,3 +279,20 @@ def test_bcast_2p30_partition_invariant(ctx):
     sb = b.buf[:-1].view(-1, 2).sum(1)
     want = float(torch.dot(sa, sb).item())
     assert math.isclose(zs[0], want, rel_tol=1e-11)
+
+
+def test_too_big_and_too_many_operands(ctx):
+    """limits are refused with the documented codes before anything is launched or allocated"""
+    from bnpp_b200 import capi
+    fake = 0x10000000          # never dereferenced: planning fails first
+    wide = list(range(33))
+    with pytest.raises(capi.BnppError) as e:      # 2^33-entry output: the reference's `unsigned` sizes cannot hold it either
+        ctx.product_sum_out([(fake, wide, [2] * 33, None)], wide, [2] * 33, None, fake)
+    assert e.value.code == -4
+    ops = [(fake, [0], [2], None)] * 7
+    with pytest.raises(capi.BnppError) as e:      # more than BNPP_MAX_OPERANDS tables in one launch
+        ctx.product_sum_out(ops, [0], [2], None, fake)
+    assert e.value.code == -3
+    with pytest.raises(capi.BnppError) as e:      # divide needs exactly two operands
+        ctx.product_sum_out(ops[:3], [0], [2], None, fake, divide=True)
+    assert e.value.code == -1

@@ -93,3 +93,11 @@ def test_fast_orderer_equals_reference_containers(golden_orders):
             fast = model.elim_order(cards, scopes, allv, case["flag"], observed=obs)
             slow = model.elim_order(cards, scopes, allv, case["flag"], reference_containers=True, observed=obs)
             assert fast == slow == (case["order"], case["width"]), (name, case["flag"])
+
+
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: the header must compile as C99 on its own"""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "bnpp_b200.h"\nint main(void) { bnpp_scope s = {0, 0, 0}; return (int)bnpp_scope_size(&s) * 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
