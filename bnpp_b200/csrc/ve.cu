@@ -62,6 +62,7 @@ struct bnpp_ve_plan {
     // replay state: one resolved launch per step and a fixed arena for the intermediates, so a
     // run is pointer patching + cudaLaunchKernel (the host must not be what small steps wait for)
     std::vector<bnpp::LaunchDesc> exec;
+    std::vector<char> exec_planned;
     std::vector<uint64_t> arena_off;        // per PlanFactor, in doubles
     uint64_t arena_doubles = 0;
     double *arena = nullptr;
@@ -319,45 +320,51 @@ void build_exec(bnpp_ve_plan *pl)
             if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) give(pl->arena_off[id], pl->f[id].size);
     }
 
+    // launches are resolved lazily, step by step, during the first run (plan_step): the GPU already
+    // executes the early buckets while the host is still resolving the later ones
+    pl->exec.assign(pl->steps.size(), LaunchDesc());
+    pl->exec_planned.assign(pl->steps.size(), 0);
+    pl->exec_ok = true;
+}
+
+// resolve the launch of step s against stand-in pointers that carry only the guaranteed alignment
+bool plan_step(bnpp_ve_plan *pl, size_t s)
+{
     double *const arena_standin = reinterpret_cast<double *>(uintptr_t(1) << 32);
     double *const table_standin = reinterpret_cast<double *>(uintptr_t(2) << 32);
     double *const result_standin = reinterpret_cast<double *>((uintptr_t(3) << 32) + 8);   // only 8-byte alignment assumed
-    pl->exec.assign(pl->steps.size(), LaunchDesc());
-    pl->exec_ok = true;
-    for (size_t s = 0; s < pl->steps.size() && pl->exec_ok; ++s) {
-        const PlanStep &st = pl->steps[s];
-        bnpp_operand ops[kMaxK];
-        for (size_t q = 0; q < st.operands.size(); ++q) {
-            const PlanFactor &pf = pl->f[st.operands[q]];
-            if (pf.src < 0) {
-                ops[q].data = arena_standin + pl->arena_off[st.operands[q]];
-            } else {
-                uint64_t g = 4;
-                for (auto &o : pf.obs) g = std::__gcd<uint64_t>(g, (uint64_t)o.first);
-                ops[q].data = table_standin + (g >= 4 ? 0 : g);
-            }
-            ops[q].scope.rank = (int32_t)pf.var.size();
-            ops[q].scope.var_id = pf.var.data();
-            ops[q].scope.card = pf.card.data();
-            ops[q].stride = pf.stride.empty() ? nullptr : pf.stride.data();
-        }
-        bnpp_scope os;
-        double *dst;
-        if (st.out == -2) {
-            os.rank = (int32_t)st.rvar.size();
-            os.var_id = st.rvar.data();
-            os.card = st.rcard.data();
-            dst = result_standin;
+    const PlanStep &st = pl->steps[s];
+    bnpp_operand ops[kMaxK];
+    for (size_t q = 0; q < st.operands.size(); ++q) {
+        const PlanFactor &pf = pl->f[st.operands[q]];
+        if (pf.src < 0) {
+            ops[q].data = arena_standin + pl->arena_off[st.operands[q]];
         } else {
-            const PlanFactor &of = pl->f[st.out];
-            os.rank = (int32_t)of.var.size();
-            os.var_id = of.var.data();
-            os.card = of.card.data();
-            dst = arena_standin + pl->arena_off[st.out];
+            uint64_t g = 4;
+            for (auto &o : pf.obs) g = std::__gcd<uint64_t>(g, (uint64_t)o.first);
+            ops[q].data = table_standin + (g >= 4 ? 0 : g);
         }
-        if (contract_plan(pl->ctx, (int)st.operands.size(), ops, &os, st.elim, 0, dst, nullptr, &pl->exec[s]) != BNPP_OK)
-            pl->exec_ok = false;
+        ops[q].scope.rank = (int32_t)pf.var.size();
+        ops[q].scope.var_id = pf.var.data();
+        ops[q].scope.card = pf.card.data();
+        ops[q].stride = pf.stride.empty() ? nullptr : pf.stride.data();
     }
+    bnpp_scope os;
+    double *dst;
+    if (st.out == -2) {
+        os.rank = (int32_t)st.rvar.size();
+        os.var_id = st.rvar.data();
+        os.card = st.rcard.data();
+        dst = result_standin;
+    } else {
+        const PlanFactor &of = pl->f[st.out];
+        os.rank = (int32_t)of.var.size();
+        os.var_id = of.var.data();
+        os.card = of.card.data();
+        dst = arena_standin + pl->arena_off[st.out];
+    }
+    pl->exec_planned[s] = 1;
+    return contract_plan(pl->ctx, (int)st.operands.size(), ops, &os, st.elim, 0, dst, nullptr, &pl->exec[s]) == BNPP_OK;
 }
 
 }  // namespace
@@ -747,6 +754,7 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             for (size_t q = 0; q < st.operands.size(); ++q) in[q] = ptr[st.operands[q]];
             double *dst = st.out == -2 ? result_dev + st.roff : pl->arena + pl->arena_off[st.out];
             double *z = (st.out == -2 && st.want_z) ? z_dev : nullptr;
+            if (!pl->exec_planned[s] && !plan_step(pl, s)) return fail(ctx, BNPP_EINVAL, "VE plan: a step could not be resolved");
             if (!(graphed && pl->use_graph)) {
                 rc = contract_launch(ctx, pl->exec[s], in, dst, z);
                 continue;
