@@ -209,3 +209,26 @@ def test_marginals_bucket_tree_vs_passes_wide(ctx):
     for v, (a, b) in enumerate(zip(fast, slow)):
         assert np.allclose(a, b, rtol=REL, atol=1e-300), v
     bn.close()
+
+
+def test_evidence_batch_sliced(ctx):
+    """a batch whose widest intermediate would exceed the slice budget is processed in slices of the batch"""
+    import random
+    import torch
+    N, nobs, nsets = 48, 4, 4096
+    bn = load(ctx, synth.random_bn_uai(N, 30, 3, 5))
+    evs = synth.evidence_batch(N, nobs, nsets, seed=9, fixed_ids=True)
+    observed = sorted(evs[0])
+    vals = torch.tensor([[ev[v] for v in observed] for ev in evs], dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    for rep in range(3):                 # plain run, captured run, replayed run
+        z = bn.partition_batch(observed, vals, "mf")
+        ctx.sync()
+        zh = z.cpu().numpy()
+        rng = random.Random(rep)
+        for i in rng.sample(range(nsets), 6) + [0, nsets - 1]:
+            zi, _ = bn.partition(evs[i], "mf")
+            assert zi == zh[i], (rep, i)
+    p = [pl for pl in bn._plans.values()][0]
+    assert p.max_step_entries * nsets > (1 << 27)      # i.e. slicing really happened
+    bn.close()
