@@ -166,7 +166,7 @@ def test_cli_byte_compat(files, golden_models, tmp_path):
         ("bn", [files["asia"]], "roots\nleaves\nwidth\nstats\nhelp\nbogus\nquit\n"),
         # prompt `query` without -ve: BN::query = joint table, then sum-outs and a divide (code/model.cpp:147-202)
         ("bn", [files["asia"]], "query 0\nquery 1 | 0\nquery 5 | 2, 3\nquery 7, 6 | 1\nquit\n"),
-        ("bn", [files["cancer"]], "query 4 | 0, 1\nquery 2\nblanket 2\nind 0,1\nind 0,1|2\nquit\n"),
+        ("bn", [files["cancer"]], "query 4 | 0, 1\nquery 2\nind 0,1\nind 0,1|2\nquit\n"),
         ("bn", [files["asia"], "-v"], "width\nquit\n"),
         ("mn", [files["grid3x3"], str(gev)], "PR\nMAR\nquit\n"),
     ]
