@@ -64,7 +64,6 @@ int bnpp_ctx_create(int device, void *stream, bnpp_ctx **out)
     BNPP_CUDA(ctx, cudaMalloc(&ctx->ticket, 64));
     BNPP_CUDA(ctx, cudaMemset(ctx->ticket, 0, 64));
     ctx->status = ctx->ticket + 4;
-    BNPP_CUDA(ctx, cudaMalloc(&ctx->scratch_z, 64));
     *out = ctx;
     return BNPP_OK;
 }
@@ -76,7 +75,6 @@ int bnpp_ctx_destroy(bnpp_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->partials);
     cudaFree(ctx->ticket);
-    cudaFree(ctx->scratch_z);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return BNPP_OK;

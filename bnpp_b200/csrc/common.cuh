@@ -112,7 +112,6 @@ struct bnpp_ctx {
     double *partials = nullptr;        // kMaxPartials doubles
     unsigned int *ticket = nullptr;    // last-block ticket, zero between launches
     unsigned int *status = nullptr;    // BNPP_STATUS_* bits
-    double *scratch_z = nullptr;       // one double for callers that pass z_dev == NULL
     uint64_t launches = 0;
     std::string last_error;
     std::string last_kernel;
