@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "contract.hpp"
 
 namespace bnpp {
 int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope, int64_t elim_var, int divide,
@@ -104,7 +105,10 @@ int bnpp_last_launch(const bnpp_ctx *ctx, char *name, size_t name_len, uint32_t 
 {
     if (!ctx) return BNPP_EINVAL;
     if (name && name_len) {
-        strncpy(name, ctx->last_kernel.c_str(), name_len - 1);
+        // valid right after the launch it describes (one-shot descriptors live on the caller's stack)
+        const std::string nm = !ctx->last_kernel.empty() ? ctx->last_kernel
+                               : (ctx->last_desc ? static_cast<bnpp::LaunchDesc *>(ctx->last_desc)->name() : std::string());
+        strncpy(name, nm.c_str(), name_len - 1);
         name[name_len - 1] = 0;
     }
     if (grid) *grid = ctx->last_grid;

@@ -115,6 +115,7 @@ struct bnpp_ctx {
     uint64_t launches = 0;
     std::string last_error;
     std::string last_kernel;
+    void *last_desc = nullptr;         // bnpp::LaunchDesc of the most recent contraction (name formatted on demand)
     uint32_t last_grid = 0, last_block = 0;
 };
 

@@ -712,30 +712,31 @@ static uint64_t resident_ctas(bnpp_ctx *ctx, F fn)
     return (uint64_t)ctx->sm_count * it->second;
 }
 
-static void note_launch(bnpp_ctx *ctx, const ParamsHead &h, const char *variant, int k, int C, int V, int U, bool div,
-                        bool generic, uint32_t R, uint64_t blocks)
-{
-    ctx->launches++;
-    char nm[128];
-    if (generic) snprintf(nm, sizeof nm, "contract_generic<%s,K=%d,div=%d> cx=%u R=%u", variant, k, div, h.cx, R);
-    else snprintf(nm, sizeof nm, "contract_fast<%s,K=%d,C=%d,V=%d,U=%d,div=%d> R=%u cls=%d,%d,%d", variant, k, C, V, U, div, R,
-                  h.cls[0], k > 1 ? h.cls[1] : -1, k > 2 ? h.cls[2] : -1);
-    ctx->last_kernel = nm;
-    ctx->last_grid = (uint32_t)blocks;
-    ctx->last_block = kBlock;
-}
-
 static void describe(LaunchDesc *d, const ParamsHead &h, const void *fn, uint64_t blocks, const char *variant, int k, int C,
                      int V, int U, bool div, bool generic, uint32_t R)
 {
     d->fn = fn;
     d->grid = (unsigned)blocks;
     d->k = k;
+    // the printable name is formatted only when somebody asks for it (LaunchDesc::name())
+    d->variant = variant;
+    d->C = C;
+    d->V = V;
+    d->U = U;
+    d->div = div;
+    d->generic = generic;
+    d->R = R;
+    (void)h;
+}
+
+std::string LaunchDesc::name()
+{
+    const ParamsHead &h = head();
     char nm[128];
     if (generic) snprintf(nm, sizeof nm, "contract_generic<%s,K=%d,div=%d> cx=%u R=%u", variant, k, div, h.cx, R);
     else snprintf(nm, sizeof nm, "contract_fast<%s,K=%d,C=%d,V=%d,U=%d,div=%d> R=%u cls=%d,%d,%d", variant, k, C, V, U, div, R,
                   h.cls[0], k > 1 ? h.cls[1] : -1, k > 2 ? h.cls[2] : -1);
-    d->name = nm;
+    return nm;
 }
 
 template <class P>
@@ -800,7 +801,8 @@ int contract_launch(bnpp_ctx *ctx, LaunchDesc &d, const double *const *in, doubl
     args[0] = d.p2 ? (d.staged ? static_cast<void *>(&d.p2p) : static_cast<void *>(&d.p2p.b)) : static_cast<void *>(&d.mrp);
     BNPP_CUDA(ctx, cudaLaunchKernel(d.fn, dim3(d.grid), dim3(kBlock), args, 0, ctx->stream));
     ctx->launches++;
-    ctx->last_kernel = d.name;
+    ctx->last_desc = &d;
+    ctx->last_kernel.clear();
     ctx->last_grid = d.grid;
     ctx->last_block = kBlock;
     return BNPP_OK;
@@ -814,7 +816,10 @@ int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *ou
     if (rc != BNPP_OK) return rc;
     const double *in[kMaxK];
     for (int q = 0; q < k; ++q) in[q] = ops[q].data;
-    return contract_launch(ctx, d, in, out_dev, z_dev);
+    const int rc2 = contract_launch(ctx, d, in, out_dev, z_dev);
+    ctx->last_kernel = d.name();      // the descriptor dies here: keep the printable name, not the pointer
+    ctx->last_desc = nullptr;
+    return rc2;
 }
 
 int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope, int64_t elim_var,
@@ -942,7 +947,7 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
     // binary axes innermost first: b[0] is the V bit, b[1..10] the item bits of a 1024-item chunk
     int staged = -1;
     std::vector<Axis> bin;
-    if (cx <= 2 && !divide && k <= 3) {
+    if (cx <= 2 && !divide && k <= 3 && n_out >= (1u << 11)) {
         bool p2all = true;
         for (const Axis &a : it) p2all = p2all && is_pow2(a.ext);
         if (p2all) {

@@ -73,7 +73,12 @@ struct LaunchDesc {
     int k = 0;
     ParamsP2S p2p;              // .b is the plain power-of-two block
     ParamsMR mrp;
-    std::string name;
+    // pieces of the printable name (formatted lazily: a VE query launches hundreds of these)
+    const char *variant = "";
+    int C = 0, V = 0, U = 0;
+    bool div = false, generic = false;
+    uint32_t R = 0;
+    std::string name();
     ParamsHead &head() { return p2 ? p2p.b.h : mrp.h; }
 };
 

@@ -696,7 +696,7 @@ static int run_dynamic(bnpp_ve_plan *pl, const std::vector<const double *> &ptr_
         rc = contract(ctx, (int)st.operands.size(), ops, &os, st.elim, 0, dst, (st.out == -2 && st.want_z) ? z_dev : nullptr);
         if (pl->profiling) {
             pl->step_kernel.resize(pl->steps.size());
-            pl->step_kernel[s] = ctx->last_kernel;
+            pl->step_kernel[s] = ctx->last_kernel;   // set by contract() below
         }
         for (int id : st.operands)
             if (owned[id] && pl->f[id].last_use == (int)s) {
@@ -784,11 +784,12 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             if (fresh) BNPP_CUDA(ctx, cudaGraphInstantiate(&pl->graph_exec, pl->graph, 0));
             BNPP_CUDA(ctx, cudaGraphLaunch(pl->graph_exec, ctx->stream));
             ctx->launches += pl->steps.size();
-            ctx->last_kernel = pl->exec.back().name;
+            ctx->last_desc = &pl->exec.back();
+            ctx->last_kernel.clear();
         }
         if (pl->profiling) {
             pl->step_kernel.resize(pl->steps.size());
-            for (size_t s = 0; s < pl->steps.size(); ++s) pl->step_kernel[s] = pl->exec[s].name;
+            for (size_t s = 0; s < pl->steps.size(); ++s) pl->step_kernel[s] = pl->exec[s].name();
         }
     }
     if (rc == BNPP_OK && pl->is_mar)
