@@ -27,6 +27,7 @@ import json
 import os
 import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -50,45 +51,41 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler:
-    """`nvidia-smi -lms` in the background while the timed regions run (B200_PROFILING.md recipe):
-    SM clock under load and the throttle reasons seen."""
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons, sampled back to back from just before the timed
+    regions until after them (B200_PROFILING.md recipe; one-shot queries: `-lms` output is
+    block-buffered into a pipe and lost on terminate)."""
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
+        super().__init__(daemon=True)
         self.index = index
-        self.proc = None
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
 
-    def start(self):
+    def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
-
-    def summary(self):
-        samples, reasons, max_mhz = [], set(), None
-        if self.proc is not None:
-            self.proc.terminate()
+        while not self.stop_flag:
             try:
-                out, _ = self.proc.communicate(timeout=5)
-            except Exception:
-                out = ""
-            for line in out.splitlines():
-                f = [x.strip() for x in line.split(",")]
-                try:
-                    samples.append(float(f[0]))
-                    max_mhz = float(f[1])
-                except (ValueError, IndexError):
-                    continue
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
                 for nm, v in zip(self.NAMES, f[2:]):
                     if v.lower().startswith("active"):
-                        reasons.add(nm)
-        s = sorted(samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": max_mhz, "reasons": sorted(reasons),
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(s)}
 
 
