@@ -219,6 +219,15 @@ def main():
     torch.cuda.set_device(local)
     ctx = capi.Context(local)
     stream = ctx.torch_stream
+    shard_comm = None
+    if world > 1:
+        from bnpp_b200.nccl import ShardComm
+        shard_comm = ShardComm(ctx, rank, world)     # the product's own NCCL communicator for the one collective of the path
+        with torch.cuda.stream(stream):
+            warm = torch.zeros(1, dtype=torch.float64, device="cuda")
+        for _ in range(3):                           # NCCL builds its channels on the first collective: not part of a step
+            shard_comm.allreduce_sum(warm.data_ptr(), 1)
+        ctx.sync()
 
     n_gpus = world
     if n_gpus not in WIDE:
@@ -262,7 +271,8 @@ def main():
     if world > 1:
         with torch.cuda.stream(stream):
             zall = res[1:].clone()
-            dist.all_reduce(zall)       # cross-shard sum-out of the shard variables: one double over NVLink
+        # cross-shard sum-out of the shard variables: one double over NVLink, through bnpp_shard_allreduce_sum
+        shard_comm.allreduce_sum(zall.data_ptr(), 1)
     e1.record(stream)
     torch.cuda.synchronize()
     if world > 1:

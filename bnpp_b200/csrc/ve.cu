@@ -959,6 +959,46 @@ int bnpp_elim_order(int nvars, const uint32_t *card, int nfac, const bnpp_scope 
     return BNPP_OK;
 }
 
+// The g variables of the widest elimination clique that `order` eliminates last:
+// with the canonical layout they are the leading axes of every wide table, so fixing them to
+// a rank's values selects that rank's slab.  scopes: factor scopes (conditioned); host only.
+int bnpp_pick_shard_vars(int nfac, const bnpp_scope *scopes, int n_order, const uint32_t *order, int g, uint32_t *out)
+{
+    if (nfac < 0 || n_order < 0 || g < 0 || (g > 0 && !out)) return BNPP_EINVAL;
+    std::map<uint32_t, int> rank;
+    for (int i = 0; i < n_order; ++i) rank[order[i]] = i;
+    std::vector<std::vector<std::vector<uint32_t>>> bucket(n_order);
+    auto place = [&](const std::vector<uint32_t> &sc) {
+        int best = -1;
+        for (uint32_t v : sc) {
+            auto it = rank.find(v);
+            if (it != rank.end() && (best < 0 || it->second < best)) best = it->second;
+        }
+        if (best >= 0) bucket[best].push_back(sc);
+    };
+    for (int f = 0; f < nfac; ++f) {
+        std::vector<uint32_t> sc;
+        for (int i = 0; i < scopes[f].rank; ++i)
+            if (rank.count(scopes[f].var_id[i])) sc.push_back(scopes[f].var_id[i]);
+        place(sc);
+    }
+    std::vector<uint32_t> widest;
+    for (int i = 0; i < n_order; ++i) {
+        if (bucket[i].empty()) continue;
+        std::vector<uint32_t> u;
+        for (auto &sc : bucket[i])
+            for (uint32_t v : sc)
+                if (std::find(u.begin(), u.end(), v) == u.end()) u.push_back(v);
+        if (u.size() > widest.size()) widest = u;
+        u.erase(std::remove(u.begin(), u.end(), order[i]), u.end());
+        place(u);
+    }
+    std::sort(widest.begin(), widest.end(), [&](uint32_t a, uint32_t b) { return rank[a] < rank[b]; });
+    const int n = (int)widest.size() < g ? (int)widest.size() : g;
+    for (int i = 0; i < n; ++i) out[i] = widest[widest.size() - n + i];
+    return n;
+}
+
 int bnpp_order_width(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_order,
                      const uint32_t *order, uint32_t *width_out)
 {

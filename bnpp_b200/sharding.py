@@ -51,3 +51,16 @@ def shard_count(shard_vars, cards=None):
     for v in shard_vars:
         n *= 2 if cards is None else int(cards[v])
     return n
+
+
+def pick_shard_vars_c(scopes, cards, order, g):
+    """the same choice through the C ABI (bnpp_pick_shard_vars), for C / C++ callers"""
+    import ctypes
+    from . import capi, model
+    L = capi.lib()
+    arr, keep = model._scopes(scopes, cards)
+    od = capi._u32(order)
+    out = (ctypes.c_uint32 * max(1, g))()
+    L.bnpp_pick_shard_vars.argtypes = [ctypes.c_int, ctypes.POINTER(capi.Scope), ctypes.c_int, capi.c_u32p, ctypes.c_int, capi.c_u32p]
+    n = L.bnpp_pick_shard_vars(len(scopes), arr, len(order), ctypes.cast(od, capi.c_u32p), g, ctypes.cast(out, capi.c_u32p))
+    return list(out[:n])

@@ -142,6 +142,11 @@ int bnpp_reduce(bnpp_ctx *ctx, int op, uint64_t n, const double *in_dev, double 
 int bnpp_elim_order(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_obs,
                     const uint32_t *obs_var, int n_vars_to_order, const uint32_t *vars, int heuristic,
                     uint32_t *order_out, uint32_t *n_order_out, uint32_t *width_out);
+/* Wide-factor sharding over G = 2^g GPUs (no reference counterpart): the g variables of
+ * the widest elimination clique that `order` eliminates last.  Every rank then runs the ordinary
+ * plan with these variables observed at its rank's values; bnpp_shard_allreduce_sum
+ * (bnpp_b200_nccl.h) sums them out across ranks.  Host only; returns how many were written. */
+int bnpp_pick_shard_vars(int nfac, const bnpp_scope *scopes, int n_order, const uint32_t *order, int g, uint32_t *out);
 /* Graph::order_width, code/graph.cpp:197-237 (host). */
 int bnpp_order_width(int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_order,
                      const uint32_t *order, uint32_t *width_out);

@@ -232,3 +232,18 @@ def test_evidence_batch_sliced(ctx):
     p = [pl for pl in bn._plans.values()][0]
     assert p.max_step_entries // 2 * nsets > (1 << 27)      # widest intermediate x batch over the slice budget: >= 2 slices
     bn.close()
+
+
+def test_shard_allreduce_single_rank(ctx):
+    """the C-ABI collective (libbnpp_b200_nccl.so) on a one-rank communicator: identity, in place,
+    on the context's stream; multi-rank sums are exercised by `bench.py --gpus N`"""
+    import torch
+    from bnpp_b200.nccl import ShardComm
+    comm = ShardComm(ctx, 0, 1)
+    with torch.cuda.stream(ctx.torch_stream):
+        buf = torch.arange(5, dtype=torch.float64, device="cuda") + 0.25
+    want = buf.clone()
+    comm.allreduce_sum(buf.data_ptr(), 5)
+    ctx.sync()
+    assert torch.equal(buf, want)
+    comm.close()

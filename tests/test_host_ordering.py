@@ -101,3 +101,20 @@ def test_header_is_plain_c(tmp_path):
     src = tmp_path / "t.c"
     src.write_text('#include "bnpp_b200.h"\nint main(void) { bnpp_scope s = {0, 0, 0}; return (int)bnpp_scope_size(&s) * 0; }\n')
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)])
+
+
+def test_shard_vars_c_equals_python():
+    """wide-factor shard variables: the C ABI (bnpp_pick_shard_vars) and the Python helper agree"""
+    from bnpp_b200 import sharding
+    for (N, W, K, seed) in [(64, 40, 4, 5), (68, 40, 4, 27), (72, 40, 4, 23), (76, 44, 4, 3), (30, 14, 3, 4)]:
+        scopes, _ = synth.random_bn_scopes(N, W, K, seed)
+        order, _w = model.elim_order([2] * N, scopes, list(range(N)), "mf")
+        for g in (0, 1, 2, 3):
+            assert sharding.pick_shard_vars(scopes, order, g) == sharding.pick_shard_vars_c(scopes, [2] * N, order, g)
+
+
+def test_nccl_library_exports():
+    so = os.path.join(ROOT, "bnpp_b200", "libbnpp_b200_nccl.so")
+    assert os.path.exists(so)
+    out = __import__("subprocess").run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+    assert " T bnpp_shard_allreduce_sum" in out
