@@ -16,6 +16,7 @@
 // bucket then has the eliminated variable as its fastest axis (32-byte loads) and
 // scopes are mutually order-compatible (pure broadcasts, no transposes).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <vector>
@@ -24,6 +25,7 @@
 #include "common.cuh"
 #include "contract.hpp"
 #include "elim_order.hpp"
+#include "fused.hpp"
 
 namespace bnpp {
 int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope, int64_t elim_var, int divide,
@@ -49,11 +51,25 @@ struct PlanStep {
     int64_t elim = -1;
     uint64_t union_entries = 0, bytes = 0;
 };
+
+// K9: the plan compiled into the step program of fused.hpp (one launch for the whole plan)
+struct FusedProgram {
+    bool built = false, ok = false;
+    std::vector<uint32_t> prog, offtab;
+    std::vector<std::pair<uint32_t, int>> ptr_slots;    // (first word of a CPT operand record, input table it views)
+    std::vector<const double *> tables;                 // the table addresses `prog` holds right now
+    uint32_t n_steps = 0, arena = 0, max_out = 0;
+    uint32_t *prog_dev = nullptr, *offtab_dev = nullptr;
+    bool offtab_uploaded = false;
+};
 }  // namespace bnpp
 
 struct bnpp_ve_plan {
     bnpp_ctx *ctx = nullptr;
     int n_inputs = 0;
+    int n_obs = 0;
+    int fused_mode = 1;                     // 0: one launch per bucket always; 1: one launch per plan when every step is small
+    bnpp::FusedProgram fused;
     std::vector<bnpp::PlanFactor> f;
     std::vector<bnpp::PlanStep> steps;
     std::vector<uint32_t> result_var, result_card;
@@ -367,6 +383,304 @@ bool plan_step(bnpp_ve_plan *pl, size_t s)
     return contract_plan(pl->ctx, (int)st.operands.size(), ops, &os, st.elim, 0, dst, nullptr, &pl->exec[s]) == BNPP_OK;
 }
 
+
+// ---- K9: compile the plan into one fused launch (fused.hpp) -------------------------------------
+constexpr uint64_t kFusedMaxUnion = 1ull << 14;      // widest step (union entries) a fused plan may contain
+constexpr uint64_t kFusedMaxTabWords = 1ull << 24;   // operand-offset tables, all steps
+constexpr size_t kFusedSmemLimit = 200u << 10;       // dynamic shared memory of one CTA
+
+bool fused_default_on()
+{
+    static const int on = [] {
+        const char *e = getenv("BNPP_FUSED");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    return on != 0;
+}
+
+// Step order: the bucket tree is walked depth first, at every node the child whose subtree needs
+// the most scratch beyond its own result first (Sethi-Ullman), so few intermediates are alive
+// at any time -- the arena of one evidence set has to fit in shared memory many times over.
+// Any topological order gives the same numbers: operand lists, hence the order of the
+// multiplications inside a bucket, are untouched.
+void fused_build(bnpp_ve_plan *pl)
+{
+    FusedProgram &fp = pl->fused;
+    fp.built = true;
+    fp.ok = false;
+    const size_t ns = pl->steps.size();
+    if (ns == 0 || ns >= (1u << 24)) return;
+    if (!pl->is_mar && pl->steps.back().out != -2) return;      // the result is the scalar 1: nothing to fuse
+    for (const PlanStep &st : pl->steps)
+        if (st.union_entries > kFusedMaxUnion || st.operands.empty() || (int)st.operands.size() > kMaxK) return;
+
+    std::vector<int> producer(pl->f.size(), -1);
+    for (size_t s = 0; s < ns; ++s)
+        if (pl->steps[s].out >= 0) producer[pl->steps[s].out] = (int)s;
+    auto out_size = [&](size_t s) -> uint64_t {
+        const PlanStep &st = pl->steps[s];
+        return st.out >= 0 ? pl->f[st.out].size : table_size(st.rcard);
+    };
+    std::vector<char> consumed(ns, 0);
+    std::vector<std::vector<int>> kids(ns);
+    std::vector<uint64_t> need(ns, 0);
+    for (size_t s = 0; s < ns; ++s) {
+        for (int id : pl->steps[s].operands) {
+            const int c = producer[id];
+            if (c < 0) continue;
+            if (c >= (int)s) return;                              // producers precede consumers in a plan
+            consumed[c] = 1;
+            if (std::find(kids[s].begin(), kids[s].end(), c) == kids[s].end()) kids[s].push_back(c);
+        }
+        std::stable_sort(kids[s].begin(), kids[s].end(), [&](int a, int b) {
+            return (int64_t)(need[a] - out_size(a)) > (int64_t)(need[b] - out_size(b));
+        });
+        uint64_t held = 0, peak = 0;
+        for (int c : kids[s]) {
+            peak = std::max(peak, held + need[c]);
+            held += out_size(c);
+        }
+        need[s] = std::max(peak, held + (pl->steps[s].out >= 0 ? out_size(s) : 0));
+    }
+    std::vector<int> order;
+    std::vector<char> done(ns, 0);
+    for (size_t root = 0; root < ns; ++root) {
+        if (done[root] || (pl->steps[root].out != -2 && consumed[root])) continue;
+        std::vector<std::pair<int, size_t>> stack{{(int)root, 0}};
+        while (!stack.empty()) {
+            const int s = stack.back().first;
+            if (stack.back().second < kids[s].size()) {
+                const int c = kids[s][stack.back().second++];
+                if (!done[c]) {
+                    done[c] = 1;
+                    stack.push_back({c, 0});
+                }
+            } else {
+                order.push_back(s);
+                stack.pop_back();
+            }
+        }
+        done[root] = 1;
+    }
+    if (order.size() != ns) return;
+
+    // arena of one evidence set: first fit over the new order, in doubles
+    std::vector<int> pos(ns, 0), last_use(pl->f.size(), -1);
+    for (size_t i = 0; i < ns; ++i) pos[order[i]] = (int)i;
+    for (size_t s = 0; s < ns; ++s)
+        for (int id : pl->steps[s].operands)
+            if (pl->f[id].src < 0) last_use[id] = std::max(last_use[id], pos[s]);
+    std::vector<uint64_t> aoff(pl->f.size(), 0);
+    std::vector<std::pair<uint64_t, uint64_t>> free_list;   // (offset, size)
+    uint64_t top = 0, peak = 0;
+    auto take = [&](uint64_t n) {
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].second >= n) {
+                const uint64_t off = free_list[i].first;
+                free_list[i].first += n;
+                free_list[i].second -= n;
+                if (!free_list[i].second) free_list.erase(free_list.begin() + i);
+                return off;
+            }
+        const uint64_t off = top;
+        top += n;
+        return off;
+    };
+    auto give = [&](uint64_t off, uint64_t n) {
+        free_list.push_back({off, n});
+        std::sort(free_list.begin(), free_list.end());
+        for (size_t i = 0; i + 1 < free_list.size();)
+            if (free_list[i].first + free_list[i].second == free_list[i + 1].first) {
+                free_list[i].second += free_list[i + 1].second;
+                free_list.erase(free_list.begin() + i + 1);
+            } else ++i;
+        if (!free_list.empty() && free_list.back().first + free_list.back().second == top) {
+            top = free_list.back().first;
+            free_list.pop_back();
+        }
+    };
+    for (size_t i = 0; i < ns; ++i) {
+        const PlanStep &st = pl->steps[order[i]];
+        if (st.out >= 0) {
+            aoff[st.out] = take(pl->f[st.out].size);
+            peak = std::max(peak, top);
+        }
+        std::vector<int> seen;
+        for (int id : st.operands) {
+            if (pl->f[id].src >= 0 || last_use[id] != (int)i || std::find(seen.begin(), seen.end(), id) != seen.end()) continue;
+            seen.push_back(id);
+            give(aoff[id], pl->f[id].size);
+        }
+        if (st.out >= 0 && last_use[st.out] < 0) give(aoff[st.out], pl->f[st.out].size);   // never read
+    }
+    if (peak >= (1ull << 24)) return;
+
+    // the program and the operand-offset tables
+    fp.prog.clear();
+    fp.offtab.clear();
+    fp.ptr_slots.clear();
+    fp.max_out = 0;
+    for (size_t i = 0; i < ns; ++i) {
+        const PlanStep &st = pl->steps[order[i]];
+        const std::vector<uint32_t> &ovar = st.out == -2 ? st.rvar : pl->f[st.out].var;
+        const std::vector<uint32_t> &ocard = st.out == -2 ? st.rcard : pl->f[st.out].card;
+        const uint64_t n_out = table_size(ocard);
+        const int k = (int)st.operands.size(), wr = (int)ovar.size();
+        if (n_out > kFusedMaxUnion) return;
+        if (fp.offtab.size() + (uint64_t)k * n_out > kFusedMaxTabWords) return;
+        fp.max_out = std::max<uint32_t>(fp.max_out, (uint32_t)n_out);
+        uint32_t cx = 1;
+        std::vector<std::vector<uint64_t>> axs(k, std::vector<uint64_t>(wr, 0));
+        std::vector<uint64_t> sx(k, 0);
+        for (int q = 0; q < k; ++q) {
+            const PlanFactor &pf = pl->f[st.operands[q]];
+            uint64_t dense = 1;
+            for (int a = (int)pf.var.size() - 1; a >= 0; --a) {
+                const uint64_t stv = pf.stride.empty() ? dense : (uint64_t)pf.stride[a];
+                dense *= pf.card[a];
+                if (st.elim >= 0 && pf.var[a] == (uint64_t)st.elim) {
+                    sx[q] = stv;
+                    cx = pf.card[a];
+                    continue;
+                }
+                int at = -1;
+                for (int j = 0; j < wr; ++j)
+                    if (ovar[j] == pf.var[a]) { at = j; break; }
+                if (at < 0 || stv >= (1ull << 32)) return;
+                axs[q][at] = stv;
+            }
+            if (sx[q] >= (1ull << 32) || pf.obs.size() > 255) return;
+        }
+        const uint32_t tab_off = (uint32_t)fp.offtab.size();
+        fp.offtab.resize(fp.offtab.size() + (size_t)k * n_out, 0);
+        {
+            std::vector<uint32_t> digit(wr, 0);
+            for (uint64_t o = 0; o < n_out; ++o) {
+                for (int q = 0; q < k; ++q) {
+                    uint64_t off = 0;
+                    for (int a = 0; a < wr; ++a) off += (uint64_t)digit[a] * axs[q][a];
+                    if (off >= (1ull << 32)) return;
+                    fp.offtab[tab_off + (size_t)q * n_out + o] = (uint32_t)off;
+                }
+                for (int a = wr - 1; a >= 0; --a) {
+                    if (++digit[a] < ocard[a]) break;
+                    digit[a] = 0;
+                }
+            }
+        }
+        uint32_t flags = 0, out_off;
+        if (st.out == -2) {
+            flags = kFusedToResult | (st.want_z ? kFusedWantZ : 0u);
+            if (st.roff >= (1ull << 32)) return;
+            out_off = (uint32_t)st.roff;
+        } else {
+            out_off = (uint32_t)aoff[st.out];
+        }
+        const uint32_t head[kFusedHeaderWords] = {(uint32_t)n_out, cx, (uint32_t)k | (flags << 8), out_off, tab_off, 0, 0, 0};
+        fp.prog.insert(fp.prog.end(), head, head + kFusedHeaderWords);
+        for (int q = 0; q < k; ++q) {
+            const PlanFactor &pf = pl->f[st.operands[q]];
+            const uint32_t at = (uint32_t)fp.prog.size();
+            if (pf.src < 0) {
+                const uint32_t rec[kFusedOperandWords] = {0u, (uint32_t)aoff[st.operands[q]], (uint32_t)sx[q], 0u};
+                fp.prog.insert(fp.prog.end(), rec, rec + kFusedOperandWords);
+                continue;
+            }
+            const uint32_t rec[kFusedOperandWords] = {1u | ((uint32_t)pf.obs.size() << 8), 0u, (uint32_t)sx[q], 0u};
+            fp.prog.insert(fp.prog.end(), rec, rec + kFusedOperandWords);
+            fp.ptr_slots.push_back({at, pf.src});
+            for (size_t j = 0; j < pf.obs.size(); j += 2) {
+                uint32_t pair[4] = {(uint32_t)pf.obs[j].first, (uint32_t)pf.obs[j].second, 0u, 0u};
+                if (pf.obs[j].first >= (1ll << 32)) return;
+                if (j + 1 < pf.obs.size()) {
+                    if (pf.obs[j + 1].first >= (1ll << 32)) return;
+                    pair[2] = (uint32_t)pf.obs[j + 1].first;
+                    pair[3] = (uint32_t)pf.obs[j + 1].second;
+                }
+                fp.prog.insert(fp.prog.end(), pair, pair + 4);
+            }
+        }
+    }
+    if (fp.prog.size() >= (1ull << 31)) return;
+    fp.n_steps = (uint32_t)ns;
+    fp.arena = (uint32_t)std::max<uint64_t>(peak, 1);
+    fp.tables.assign(pl->n_inputs, nullptr);
+    fp.ok = true;
+}
+
+// lanes per evidence set for a run over nb sets; 0 = this run is not fused
+int fused_pick(bnpp_ve_plan *pl, uint32_t nb)
+{
+    if (!pl->fused_mode || pl->profiling) return 0;
+    FusedProgram &fp = pl->fused;
+    if (!fp.built) fused_build(pl);
+    if (!fp.ok) return 0;
+    int G = 0;
+    if (nb == 1) {
+        G = fp.max_out >= 128 ? 128 : 32;
+        if (fused_smem_bytes(G, fp.arena) > kFusedSmemLimit) G = 128;
+    } else {
+        // at least ~16 warps per SM: the arena of one warp's sets within 13.75 KB
+        for (int g : {8, 16, 32})
+            if (!G && (uint64_t)(32 / g) * fp.arena * sizeof(double) <= 14080) G = g;
+        if (!G) G = fused_smem_bytes(32, fp.arena) <= kFusedSmemLimit ? 32 : 128;
+    }
+    if (const char *e = getenv("BNPP_FUSED_G")) {
+        const int g = atoi(e);
+        if (fused_valid_g(g) && nb > 1) G = g;
+    }
+    if (fused_smem_bytes(G, fp.arena) > kFusedSmemLimit) return 0;
+    return G;
+}
+
+int run_fused(bnpp_ve_plan *pl, int G, const double *const *tables_dev, uint32_t nb, const uint8_t *ev_dev,
+              const uint32_t *obs_val, double *result_dev, double *z_dev)
+{
+    bnpp_ctx *ctx = pl->ctx;
+    FusedProgram &fp = pl->fused;
+    bool moved = fp.prog_dev == nullptr;
+    for (auto &slot : fp.ptr_slots) moved = moved || fp.tables[slot.second] != tables_dev[slot.second];
+    if (moved) {
+        for (auto &slot : fp.ptr_slots) {
+            const uint64_t a = reinterpret_cast<uint64_t>(tables_dev[slot.second]);
+            fp.prog[slot.first + 1] = (uint32_t)a;
+            fp.prog[slot.first + 3] = (uint32_t)(a >> 32);
+            fp.tables[slot.second] = tables_dev[slot.second];
+        }
+        if (!fp.prog_dev) {
+            double *store = nullptr;
+            const int rc = bnpp_alloc(ctx, fp.prog.size() / 2 + 2, &store);
+            if (rc != BNPP_OK) return rc;
+            fp.prog_dev = reinterpret_cast<uint32_t *>(store);
+        }
+        // stream-ordered after any launch still reading the previous contents; the pageable source is staged before the call returns
+        BNPP_CUDA(ctx, cudaMemcpyAsync(fp.prog_dev, fp.prog.data(), fp.prog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!fp.offtab_uploaded) {
+        double *store = nullptr;
+        const int rc = bnpp_alloc(ctx, fp.offtab.size() / 2 + 2, &store);
+        if (rc != BNPP_OK) return rc;
+        fp.offtab_dev = reinterpret_cast<uint32_t *>(store);
+        if (!fp.offtab.empty())
+            BNPP_CUDA(ctx, cudaMemcpyAsync(fp.offtab_dev, fp.offtab.data(), fp.offtab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        fp.offtab_uploaded = true;
+    }
+    FusedLaunch p;
+    memset(&p, 0, sizeof p);
+    p.prog = fp.prog_dev;
+    p.offtab = fp.offtab_dev;
+    p.ev = ev_dev;
+    p.result = result_dev;
+    p.z = nb == 1 ? z_dev : nullptr;
+    p.nb = nb;
+    p.n_obs = (uint32_t)pl->n_obs;
+    p.n_steps = fp.n_steps;
+    p.arena = fp.arena;
+    if (!ev_dev && obs_val)
+        for (int i = 0; i < pl->n_obs && i < kFusedInlineEv; ++i) p.ev_inline[i] = (uint8_t)obs_val[i];
+    return fused_launch(ctx, G, p);
+}
+
 }  // namespace
 
 extern "C" {
@@ -374,11 +688,13 @@ extern "C" {
 int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n_obs, const uint32_t *obs_var,
                         int n_order, const uint32_t *order, bnpp_ve_plan **out)
 {
-    if (!ctx || !out || nfac < 0 || n_obs < 0 || n_order < 0) return BNPP_EINVAL;
+    if (!out || nfac < 0 || n_obs < 0 || n_order < 0) return BNPP_EINVAL;   // ctx == NULL: a dry plan (inspect, never run)
     *out = nullptr;
     bnpp_ve_plan *pl = new bnpp_ve_plan();
     pl->ctx = ctx;
     pl->n_inputs = nfac;
+    pl->n_obs = n_obs;
+    pl->fused_mode = fused_default_on() ? 1 : 0;
 
     std::map<uint32_t, int> obs_index;
     for (int i = 0; i < n_obs; ++i) obs_index[obs_var[i]] = i;
@@ -453,11 +769,13 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
 int bnpp_mar_plan_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_obs,
                          const uint32_t *obs_var, int n_order, const uint32_t *order, bnpp_ve_plan **out)
 {
-    if (!ctx || !out || nvars < 0 || nfac < 0 || n_obs < 0 || n_order < 0) return BNPP_EINVAL;
+    if (!out || nvars < 0 || nfac < 0 || n_obs < 0 || n_order < 0) return BNPP_EINVAL;   // ctx == NULL: a dry plan
     *out = nullptr;
     bnpp_ve_plan *pl = new bnpp_ve_plan();
     pl->ctx = ctx;
     pl->n_inputs = nfac;
+    pl->n_obs = n_obs;
+    pl->fused_mode = fused_default_on() ? 1 : 0;
     pl->is_mar = true;
     std::map<uint32_t, int> obs_index;
     for (int i = 0; i < n_obs; ++i) obs_index[obs_var[i]] = i;
@@ -551,6 +869,10 @@ int bnpp_mar_plan_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfa
             if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) live -= 8 * pl->f[id].size;
     }
     build_exec(pl);
+    if (!ctx) {
+        *out = pl;
+        return BNPP_OK;
+    }
     double *store = nullptr;
     int rc = bnpp_alloc(ctx, (uint64_t)nvars + 2, &store);   // 2 * nvars uint32
     if (rc != BNPP_OK) {
@@ -591,6 +913,8 @@ int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
     if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
     if (pl->graph) cudaGraphDestroy(pl->graph);
     if (pl->arena) bnpp_free(pl->ctx, pl->arena);
+    if (pl->fused.prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.prog_dev));
+    if (pl->fused.offtab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.offtab_dev));
     if (pl->mar_off_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->mar_off_dev));
     for (uint32_t *t : pl->offtab_dev)
         if (t) bnpp_free(pl->ctx, reinterpret_cast<double *>(t));
@@ -627,6 +951,53 @@ int bnpp_ve_plan_set_profiling(bnpp_ve_plan *pl, int on)
             BNPP_CUDA(pl->ctx, cudaEventCreate(&e));
             pl->ev.push_back(e);
         }
+    }
+    return BNPP_OK;
+}
+
+int bnpp_ve_plan_set_fused(bnpp_ve_plan *pl, int on)
+{
+    if (!pl) return BNPP_EINVAL;
+    pl->fused_mode = on != 0;
+    return BNPP_OK;
+}
+
+int bnpp_ve_plan_fused_info(bnpp_ve_plan *pl, uint32_t nb, int32_t *lanes_per_set, uint32_t *arena_doubles, uint32_t *n_steps)
+{
+    if (!pl || nb == 0) return BNPP_EINVAL;
+    const int G = fused_pick(pl, nb);
+    if (lanes_per_set) *lanes_per_set = G;
+    if (arena_doubles) *arena_doubles = G ? pl->fused.arena : 0;
+    if (n_steps) *n_steps = G ? pl->fused.n_steps : 0;
+    return BNPP_OK;
+}
+
+// The step program a fused run over nb sets would execute (fused.hpp), for inspection and for the
+// CPU interpreter of the tests: CPT operand records carry the INDEX of their input table in word 1
+// and 0xffffffff in word 3 instead of a device address.
+int bnpp_ve_plan_fused_program(bnpp_ve_plan *pl, uint32_t nb, uint32_t *prog, uint64_t prog_cap, uint64_t *prog_words,
+                               uint32_t *offtab, uint64_t tab_cap, uint64_t *tab_words)
+{
+    if (!pl || nb == 0) return BNPP_EINVAL;
+    const bool was_profiling = pl->profiling;
+    pl->profiling = false;
+    const int G = fused_pick(pl, nb);
+    pl->profiling = was_profiling;
+    if (prog_words) *prog_words = G ? pl->fused.prog.size() : 0;
+    if (tab_words) *tab_words = G ? pl->fused.offtab.size() : 0;
+    if (!G) return BNPP_OK;
+    const FusedProgram &fp = pl->fused;
+    if (prog) {
+        if (prog_cap < fp.prog.size()) return BNPP_EINVAL;
+        std::copy(fp.prog.begin(), fp.prog.end(), prog);
+        for (auto &slot : fp.ptr_slots) {
+            prog[slot.first + 1] = (uint32_t)slot.second;
+            prog[slot.first + 3] = 0xffffffffu;
+        }
+    }
+    if (offtab) {
+        if (tab_cap < fp.offtab.size()) return BNPP_EINVAL;
+        std::copy(fp.offtab.begin(), fp.offtab.end(), offtab);
     }
     return BNPP_OK;
 }
@@ -712,7 +1083,7 @@ static int run_dynamic(bnpp_ve_plan *pl, const std::vector<const double *> &ptr_
 int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const uint32_t *obs_val, double *result_dev,
                      double *z_dev)
 {
-    if (!pl || !result_dev) return BNPP_EINVAL;
+    if (!pl || !pl->ctx || !result_dev) return BNPP_EINVAL;
     bnpp_ctx *ctx = pl->ctx;
     std::vector<const double *> ptr(pl->f.size(), nullptr);
     bool aligned32 = true;
@@ -731,7 +1102,16 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
         if (rc != BNPP_OK) return rc;
     }
     int rc = BNPP_OK;
-    if (!pl->exec_ok || !aligned32) {
+    int fused_g = 0;
+    if (pl->n_obs <= kFusedInlineEv) {
+        bool bytes = true;
+        for (int i = 0; i < pl->n_obs; ++i) bytes = bytes && obs_val[i] <= 255;
+        if (bytes) fused_g = fused_pick(pl, 1);
+    }
+    if (fused_g) {
+        // K9: every step is small -- the whole plan is one launch, intermediates in shared memory
+        rc = run_fused(pl, fused_g, tables_dev, 1, nullptr, obs_val, result_dev, z_dev);
+    } else if (!pl->exec_ok || !aligned32) {
         rc = run_dynamic(pl, ptr, result_dev, z_dev);
     } else {
         if (!pl->arena && pl->arena_doubles) {
@@ -812,8 +1192,13 @@ static int run_batched_once(bnpp_ve_plan *pl, const double *const *tables_dev, u
 int bnpp_ve_plan_run_batched(bnpp_ve_plan *pl, const double *const *tables_dev, uint32_t nb, uint32_t n_obs,
                              const uint8_t *ev_dev, double *result_dev)
 {
-    if (!pl || !result_dev || nb == 0) return BNPP_EINVAL;
+    if (!pl || !pl->ctx || !result_dev || nb == 0) return BNPP_EINVAL;
     bnpp_ctx *ctx = pl->ctx;
+    if ((int)n_obs == pl->n_obs && (ev_dev || n_obs == 0) && nb > 1) {
+        // K9: one launch for the whole batch, the intermediates of a set never leave shared memory
+        const int G = fused_pick(pl, nb);
+        if (G) return run_fused(pl, G, tables_dev, nb, ev_dev, nullptr, result_dev, nullptr);
+    }
     std::vector<const void *> key;
     key.push_back(ev_dev);
     key.push_back(result_dev);

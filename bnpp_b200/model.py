@@ -36,6 +36,8 @@ def _declare(L):
                                        capi.c_u32p, ctypes.c_int, capi.c_u32p, P(ctypes.c_void_p)]
     L.bnpp_mar_plan_layout.argtypes = [ctypes.c_void_p, ctypes.c_int, capi.c_u32p, capi.c_u32p, capi.c_u64p]
     L.bnpp_ve_plan_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.bnpp_ve_plan_set_fused.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.bnpp_ve_plan_fused_info.argtypes = [ctypes.c_void_p, ctypes.c_uint32, P(ctypes.c_int32), capi.c_u32p, capi.c_u32p]
     L.bnpp_ve_plan_step_stats.argtypes = [ctypes.c_void_p, ctypes.c_uint64, P(ctypes.c_float), capi.c_u64p, capi.c_u64p,
                                           P(ctypes.c_int32)]
     L.bnpp_ve_plan_step_kernel.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_size_t]
@@ -130,6 +132,16 @@ class VEPlan:
 
     def set_profiling(self, on=True):
         self.ctx.check(self.ctx.L.bnpp_ve_plan_set_profiling(self.h, int(on)))
+
+    def set_fused(self, on=True):
+        """one launch for the whole plan when every step is small (default), or one launch per bucket"""
+        self.ctx.check(self.ctx.L.bnpp_ve_plan_set_fused(self.h, int(on)))
+
+    def fused_info(self, nb=1):
+        """-> (lanes per evidence set, 0 = a run over nb sets is not fused; shared-memory doubles per set; steps)"""
+        g, a, n = ctypes.c_int32(), ctypes.c_uint32(), ctypes.c_uint32()
+        self.ctx.check(self.ctx.L.bnpp_ve_plan_fused_info(self.h, int(nb), ctypes.byref(g), ctypes.byref(a), ctypes.byref(n)))
+        return g.value, a.value, n.value
 
     def step_stats(self):
         n = self.n_launches

@@ -159,7 +159,9 @@ int bnpp_order_width(int nvars, const uint32_t *card, int nfac, const bnpp_scope
  *                   not in `order` are kept: the result is a table over them, ascending
  *                   variable id, last fastest (the reference leaves this order to a
  *                   pointer-keyed hash set).
- * One plan serves any number of runs (other evidence values, other table contents). */
+ * One plan serves any number of runs (other evidence values, other table contents).
+ * ctx may be NULL: a DRY plan -- planning is host work -- that can be inspected (info, layout,
+ * fused_info, fused_program) but not run (the run entry points return BNPP_EINVAL). */
 typedef struct bnpp_ve_plan bnpp_ve_plan;
 int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n_obs, const uint32_t *obs_var,
                         int n_order, const uint32_t *order, bnpp_ve_plan **out);
@@ -191,6 +193,21 @@ int bnpp_mar_plan_layout(const bnpp_ve_plan *plan, int nvars, uint32_t *off, uin
  * One launch per bucket for the whole batch; CPTs are shared, never copied per set. */
 int bnpp_ve_plan_run_batched(bnpp_ve_plan *plan, const double *const *tables_dev, uint32_t nb, uint32_t n_obs,
                              const uint8_t *ev_dev, double *result_dev);
+/* K9 -- a plan whose elimination steps are all small (every union table <= 2^14 entries: the
+ * shipped toy networks, config 1/2 queries, config 5 batches) runs as ONE launch: a group of
+ * lanes owns an evidence set and walks the bucket loop of code/model.cpp:409-439 with the
+ * intermediates of the set in shared memory; results are bit-identical to the launch-per-bucket
+ * path.  On by default (environment BNPP_FUSED=0 turns it off for new plans); set_fused(plan, 0)
+ * forces one launch per bucket.  fused_info: lanes per evidence set a run over nb sets would use
+ * (0 = not fused), shared-memory doubles per set, steps in the launch. */
+int bnpp_ve_plan_set_fused(bnpp_ve_plan *plan, int on);
+int bnpp_ve_plan_fused_info(bnpp_ve_plan *plan, uint32_t nb, int32_t *lanes_per_set, uint32_t *arena_doubles,
+                            uint32_t *n_steps);
+/* the step program of a fused run (format: bnpp_b200/csrc/fused.hpp) for inspection; CPT operand
+ * records carry the input-table index (word 1) and 0xffffffff (word 3) instead of an address.
+ * Pass NULL buffers to query the sizes.  Works on dry plans (created with ctx == NULL). */
+int bnpp_ve_plan_fused_program(bnpp_ve_plan *plan, uint32_t nb, uint32_t *prog, uint64_t prog_cap, uint64_t *prog_words,
+                               uint32_t *offtab, uint64_t tab_cap, uint64_t *tab_words);
 /* per-launch CUDA-event timing for roofline reports: enable, run, then read
  * ms / algorithmic bytes / union entries / operand count per launch (synchronises). */
 int bnpp_ve_plan_set_profiling(bnpp_ve_plan *plan, int on);

@@ -1,0 +1,111 @@
+"""K9 without a GPU: the step program a VE plan compiles itself into for the one-launch kernel
+(`ve_fused`, bnpp_b200/csrc/fused.cu) is built on a DRY plan and executed by the CPU interpreter
+of tests/fused_interp.py; the results must equal the reference's PR / MAR values (golden
+fixtures dumped from the compiled reference) within 1e-9.  This pins the host half of K9 -- the
+depth-first step order, the shared-memory arena layout, operand-offset tables, evidence folded
+into CPT base offsets; the device half is pinned by tests/test_gpu_fused.py."""
+import math
+
+import numpy as np
+import pytest
+
+from bnpp_b200 import model, synth
+from fused_interp import DryPlan, interpret, parse_uai
+
+REL = 1e-9
+SMALL = ["asia", "asia_positive", "cancer", "earthquake", "child", "alarm", "insurance", "grid3x3"]
+
+
+def _order(cards, scopes, variables, ev, flag):
+    if not flag:
+        return [v for v in variables if v not in ev]
+    return model.elim_order(cards, scopes, variables, flag, observed=sorted(ev))[0]
+
+
+def test_fused_program_partition(golden_models):
+    n = 0
+    for name in SMALL:
+        m = golden_models[name]
+        cards, scopes, tables = parse_uai(m["uai"])
+        for case in m["pr"]:
+            ev = {int(k): v for k, v in case["evidence"].items()}
+            variables = [v for v in range(len(cards)) if v not in ev]
+            order = _order(cards, scopes, variables, ev, case["flag"])
+            if case["flag"]:
+                assert order == case["order"]
+            observed = sorted(ev)
+            p = DryPlan(cards, scopes, observed, order)
+            G, arena, n_steps = p.fused_info(1)
+            if G == 0:
+                p.close()
+                continue
+            assert G in (32, 128)
+            prog, tab = p.program(1)
+            res, z = interpret(prog, tab, n_steps, arena, tables, [ev[v] for v in observed], 1)
+            assert math.isclose(res[0], case["pr"], rel_tol=REL), (name, case["flag"], res[0], case["pr"])
+            assert z == res[0]
+            p.close()
+            n += 1
+    assert n >= 40
+
+
+def test_fused_program_marginals(golden_models):
+    n = 0
+    for name in ["asia", "child", "alarm", "grid3x3"]:
+        m = golden_models[name]
+        cards, scopes, tables = parse_uai(m["uai"])
+        for case in m["mar"]:
+            ev = {int(k): v for k, v in case["evidence"].items()}
+            variables = [v for v in range(len(cards)) if v not in ev]
+            order = _order(cards, scopes, variables, ev, "mf")
+            observed = sorted(ev)
+            p = DryPlan(cards, scopes, observed, order, marginals=True)
+            G, arena, n_steps = p.fused_info(1)
+            if G == 0:
+                p.close()
+                continue
+            off, size, total = p.layout
+            prog, tab = p.program(1)
+            res, _ = interpret(prog, tab, n_steps, arena, tables, [ev[v] for v in observed], total)
+            for v, want in enumerate(case["mar"]):
+                seg = res[off[v]:off[v] + size[v]]
+                got = np.array([1.0]) if size[v] == 1 else seg / seg.sum()      # normalize_segments (elementwise.cu)
+                assert len(got) == len(want), (name, v)
+                assert np.allclose(got, want, rtol=REL, atol=1e-300), (name, v, got, want)
+            p.close()
+            n += 1
+    assert n >= 4
+
+
+def test_fused_program_batch(golden_synth):
+    """config 5's network: one program for every evidence set, only the evidence values differ"""
+    for rec in golden_synth["batch"]:
+        if not rec["fixed_ids"]:
+            continue
+        cards, scopes, tables = parse_uai(synth.random_bn_uai(rec["N"], rec["W"], rec["K"], rec["seed"]))
+        evs = synth.evidence_batch(rec["N"], rec["nobs"], rec["nsets"], seed=5, fixed_ids=True)
+        observed = sorted(evs[0])
+        variables = [v for v in range(len(cards)) if v not in evs[0]]
+        order = _order(cards, scopes, variables, evs[0], "mf")
+        p = DryPlan(cards, scopes, observed, order)
+        G, arena, n_steps = p.fused_info(4096)
+        assert G in (8, 16, 32), "config 5 must run fused"
+        assert arena * 8 * (32 // G) <= 14080
+        prog, tab = p.program(4096)
+        for i in range(0, len(evs), 4 if rec["N"] > 100 else 1):
+            res, _ = interpret(prog, tab, n_steps, arena, tables, [evs[i][v] for v in observed], 1)
+            assert math.isclose(res[0], rec["pr"][i], rel_tol=REL), (rec["N"], i)
+        # the same plan, one launch per bucket: not fused when asked
+        p.set_fused(False)
+        assert p.fused_info(4096)[0] == 0
+        p.close()
+
+
+def test_wide_plans_are_not_fused():
+    """config 4 class networks keep one launch per bucket (their tables do not fit shared memory)"""
+    scopes, _ = synth.random_bn_scopes(40, 24, 3, 3)
+    cards = [2] * 40
+    order = model.elim_order(cards, scopes, list(range(40)), "mf")[0]
+    p = DryPlan(cards, scopes, [], order)
+    assert p.fused_info(1)[0] == 0 and p.fused_info(1024)[0] == 0
+    p.close()
