@@ -59,6 +59,7 @@ struct FusedProgram {
     std::vector<std::pair<uint32_t, int>> ptr_slots;    // (first word of a CPT operand record, input table it views)
     std::vector<const double *> tables;                 // the table addresses `prog` holds right now
     uint32_t n_steps = 0, arena = 0, max_out = 0;
+    uint64_t total_union = 0;                           // union entries of all steps, per evidence set
     uint32_t *prog_dev = nullptr, *offtab_dev = nullptr;
     bool offtab_uploaded = false;
 };
@@ -386,7 +387,8 @@ bool plan_step(bnpp_ve_plan *pl, size_t s)
 
 // ---- K9: compile the plan into one fused launch (fused.hpp) -------------------------------------
 constexpr uint64_t kFusedMaxUnion = 1ull << 14;      // widest step (union entries) a fused plan may contain
-constexpr uint64_t kFusedMaxTabWords = 1ull << 24;   // operand-offset tables, all steps
+constexpr uint64_t kFusedMaxTabWords = 1ull << 21;   // operand-offset tables, all steps
+constexpr uint64_t kFusedMaxLaneWork = 1ull << 13;   // union entries one lane may walk per evidence set (the steps of a set are serial)
 constexpr size_t kFusedSmemLimit = 200u << 10;       // dynamic shared memory of one CTA
 
 bool fused_default_on()
@@ -603,6 +605,8 @@ void fused_build(bnpp_ve_plan *pl)
     }
     if (fp.prog.size() >= (1ull << 31)) return;
     fp.n_steps = (uint32_t)ns;
+    fp.total_union = 0;
+    for (const PlanStep &st : pl->steps) fp.total_union += st.union_entries;
     fp.arena = (uint32_t)std::max<uint64_t>(peak, 1);
     fp.tables.assign(pl->n_inputs, nullptr);
     fp.ok = true;
@@ -624,11 +628,15 @@ int fused_pick(bnpp_ve_plan *pl, uint32_t nb)
         for (int g : {8, 16, 32})
             if (!G && (uint64_t)(32 / g) * fp.arena * sizeof(double) <= 14080) G = g;
         if (!G) G = fused_smem_bytes(32, fp.arena) <= kFusedSmemLimit ? 32 : 128;
+        if (const char *e = getenv("BNPP_FUSED_G")) {      // experiments: force the lanes per set of batched runs
+            const int g = atoi(e);
+            if (fused_valid_g(g)) G = g;
+        }
     }
-    if (const char *e = getenv("BNPP_FUSED_G")) {
-        const int g = atoi(e);
-        if (fused_valid_g(g) && nb > 1) G = g;
-    }
+    // the steps of one set run one after the other on its G lanes: a set with much work needs a wider group,
+    // and beyond a CTA per set the launch-per-bucket path (all SMs on every step) is the better one
+    while (fp.total_union / G > kFusedMaxLaneWork && G < 128) G = G < 32 ? 2 * G : 128;
+    if (fp.total_union / G > kFusedMaxLaneWork) return 0;
     if (fused_smem_bytes(G, fp.arena) > kFusedSmemLimit) return 0;
     return G;
 }

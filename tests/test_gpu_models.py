@@ -139,6 +139,8 @@ def test_evidence_batch_one_launch_per_bucket(ctx, golden_synth):
         observed = sorted(evs[0])
         vals = torch.tensor([[ev[v] for v in observed] for ev in evs], dtype=torch.uint8, device="cuda")
         torch.cuda.synchronize()
+        plan = bn.plan(observed, bn.order([v for v in range(bn.nvars) if v not in observed], observed, "mf")[0])
+        plan.set_fused(False)               # this test is about the launch-per-bucket batch path (K8); K9: test_gpu_fused.py
         launches0 = ctx.launches
         z = bn.partition_batch(observed, vals, "mf")
         ctx.sync()

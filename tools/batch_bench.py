@@ -25,7 +25,16 @@ def main():
     ap.add_argument("--sets", type=int, default=65536)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--fused", type=int, default=1, help="1: the whole batch in one launch (K9, default); 0: one launch per bucket (K8)")
+    ap.add_argument("--lanes", type=int, default=0, help="K9: force the lanes per evidence set (8, 16, 32, 128)")
+    ap.add_argument("--ctas-per-sm", type=int, default=0, help="K9: cap on resident CTAs per SM")
     args = ap.parse_args()
+    if not args.fused:
+        os.environ["BNPP_FUSED"] = "0"
+    if args.lanes:
+        os.environ["BNPP_FUSED_G"] = str(args.lanes)
+    if args.ctas_per_sm:
+        os.environ["BNPP_FUSED_CTAS_PER_SM"] = str(args.ctas_per_sm)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if world > 1:
@@ -55,7 +64,10 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
     launches = (ctx.launches - launches0) // args.iters
-    plan_bytes = list(bn._plans.values())[0].bytes      # 8 * (sum #operands + #out) per evidence set (CPT reads included)
+    plan0 = list(bn._plans.values())[0]
+    plan_bytes = plan0.bytes      # 8 * (sum #operands + #out) per evidence set (CPT reads included)
+    fused_info = plan0.fused_info(hi - lo)
+    union_entries = plan0.union_entries
     bn.drop_plans()
     torch.cuda.synchronize()
     per_iter = []
@@ -77,6 +89,9 @@ def main():
                "e2e": {"value": args.sets / e2e_ms * 1e3, "ms_per_batch": e2e_ms, "h2d_bytes": host.numel() * world, "d2h_bytes": 8 * args.sets,
                        "ms_each": [round(x, 2) for x in per_iter]},
                "launches_per_batch": launches, "sample_Z": zh[:3].tolist(),
+               "kernel": ("ve_fused: %d lanes per set, %d doubles of shared memory per set, %d steps in the launch" % fused_info)
+               if fused_info[0] else "contract_batched: one launch per bucket",
+               "entries_per_s": union_entries * args.sets / ms * 1e3,
                "algorithmic_GB_per_batch_per_rank": plan_bytes * (hi - lo) / 1e9,
                "GBs_per_rank": plan_bytes * (hi - lo) / ms / 1e6}
         print(json.dumps(out))
