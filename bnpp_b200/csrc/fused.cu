@@ -5,8 +5,12 @@
 // evidence set by BN::partition, code/model.cpp:275-294).  A group of G lanes owns one evidence
 // set and walks the step list of fused.hpp:
 //   * the arena of a set (its live intermediates, first-fit over a depth-first step order that
-//     keeps it small) sits in shared memory, the sets of a warp interleaved entry by entry so
-//     that lanes reading consecutive entries of their sets hit consecutive banks;
+//     keeps it small) sits in shared memory.  The sets of a warp are interleaved in PAIRS of
+//     doubles -- element e of set s lives at  (e & ~1) * SPW + 2 s + (e & 1)  of the warp's slice
+//     -- and lane l of set s is thread  l * SPW + s  of the warp: lanes reading consecutive
+//     pairs of their sets then hit consecutive 16-byte slots (no bank conflicts), and the two
+//     values of a binary eliminated variable (stride 1 in every intermediate, canonical layout
+//     of ve.cu) arrive in ONE 128-bit shared load;
 //   * a resident CPT is read in place through the base offset its observed axes select
 //     (Factor::conditioning, code/factor.cpp:214-242, reduced to one multiply-add per axis);
 //   * operand offsets per output entry come from the step's table (same numbers for every set);
@@ -22,6 +26,8 @@
 
 namespace bnpp {
 
+extern __shared__ __align__(16) double arena_smem[];
+
 __device__ __forceinline__ uint4 ldg4(const uint32_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 
 template <int G>
@@ -31,103 +37,159 @@ __device__ __forceinline__ void group_sync()
     else __syncthreads();
 }
 
-// the output entries lane, lane + G, ... of one step; returns their sum
-template <int K, int CX, int G>
-__device__ __forceinline__ double fused_entries(const double *(&src)[K], const uint32_t (&mul)[K],
-                                                const uint32_t (&sxm)[K], const uint32_t *__restrict__ tab, uint32_t n_out,
-                                                uint32_t cx, uint32_t lane, double *dst, uint64_t dmul, bool store)
+// where this thread's evidence set keeps its arena, and where results go
+template <int SPW>
+struct SetView {
+    uint32_t wbase;     // index (doubles) of element 0 of the set inside arena_smem; even
+    __device__ __forceinline__ uint32_t at(uint32_t e) const { return wbase + (e & ~1u) * SPW + (e & 1u); }
+    __device__ __forceinline__ uint32_t pair(uint32_t e) const { return wbase + e * SPW; }      // e even
+};
+
+struct Operands {
+    uint32_t base[kMaxK];           // arena operand: element offset of the table inside the set's arena
+    uint32_t sx[kMaxK];             // stride of the eliminated variable
+    const double *cpt[kMaxK];       // CPT operand: the table, evidence offset applied
+};
+
+struct Dest {
+    double *result;     // != nullptr: this step writes the result buffer, entry o at result[o * stride]
+    uint64_t stride;
+    uint32_t out_off;   // arena destination: element offset
+    bool store;
+};
+
+template <int SPW>
+__device__ __forceinline__ void put(const SetView<SPW> &v, const Dest &d, uint32_t o, double val)
+{
+    if (d.result) {
+        if (d.store) d.result[(uint64_t)o * d.stride] = val;
+    } else {
+        arena_smem[v.at(d.out_off + o)] = val;
+    }
+}
+
+// Binary eliminated variable, every arena operand with the variable at stride 1 on an even
+// offset (a 16-byte pair), AMASK = which operands are arena tables -- the shape of every bucket
+// of an all-binary network.  Two output entries per trip, all loads of both before the math.
+template <int K, unsigned AMASK, int G, int SPW>
+__device__ __forceinline__ double entries_pairs(const SetView<SPW> &v, const Operands &op, const uint32_t *__restrict__ tab,
+                                                uint32_t n_out, uint32_t lane, const Dest &d)
+{
+    double zacc = 0.0;
+    for (uint32_t o0 = lane; o0 < n_out; o0 += 2 * G) {
+        const bool two = o0 + G < n_out;
+        const uint32_t o1 = two ? o0 + G : o0;
+        uint32_t off0[K], off1[K];
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+            off0[q] = __ldg(tab + (size_t)q * n_out + o0);
+            off1[q] = __ldg(tab + (size_t)q * n_out + o1);
+        }
+        double a0[K], a1[K], b0[K], b1[K];
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+            if ((AMASK >> q) & 1u) {
+                const double2 pa = *reinterpret_cast<const double2 *>(&arena_smem[v.pair(op.base[q] + off0[q])]);
+                const double2 pb = *reinterpret_cast<const double2 *>(&arena_smem[v.pair(op.base[q] + off1[q])]);
+                a0[q] = pa.x; a1[q] = pa.y;
+                b0[q] = pb.x; b1[q] = pb.y;
+            } else {
+                a0[q] = __ldg(op.cpt[q] + off0[q]);
+                a1[q] = __ldg(op.cpt[q] + off0[q] + op.sx[q]);
+                b0[q] = __ldg(op.cpt[q] + off1[q]);
+                b1[q] = __ldg(op.cpt[q] + off1[q] + op.sx[q]);
+            }
+        }
+        double x0 = a0[0], x1 = a1[0], y0 = b0[0], y1 = b1[0];
+#pragma unroll
+        for (int q = 1; q < K; ++q) {
+            x0 = __dmul_rn(x0, a0[q]);
+            x1 = __dmul_rn(x1, a1[q]);
+            y0 = __dmul_rn(y0, b0[q]);
+            y1 = __dmul_rn(y1, b1[q]);
+        }
+        const double ra = __dadd_rn(x0, x1), rb = __dadd_rn(y0, y1);
+        put<SPW>(v, d, o0, ra);
+        zacc = __dadd_rn(zacc, ra);
+        if (two) {
+            put<SPW>(v, d, o1, rb);
+            zacc = __dadd_rn(zacc, rb);
+        }
+    }
+    return zacc;
+}
+
+// any cardinality, any operand layout; amask: which operands are arena tables
+template <int K, int G, int SPW>
+__device__ __forceinline__ double entries_any(const SetView<SPW> &v, const Operands &op, uint32_t amask,
+                                              const uint32_t *__restrict__ tab, uint32_t n_out, uint32_t cx, uint32_t lane,
+                                              const Dest &d)
 {
     double zacc = 0.0;
     for (uint32_t o = lane; o < n_out; o += G) {
-        const double *ptr[K];
+        uint32_t off[K];
 #pragma unroll
-        for (int q = 0; q < K; ++q) ptr[q] = src[q] + (size_t)(__ldg(tab + (size_t)q * n_out + o) * mul[q]);
-        double acc;
-        if (CX == 1) {
-            double t[K];
-#pragma unroll
-            for (int q = 0; q < K; ++q) t[q] = *ptr[q];
-            acc = t[0];
-#pragma unroll
-            for (int q = 1; q < K; ++q) acc = __dmul_rn(acc, t[q]);
-        } else if (CX == 2) {
-            double t0[K], t1[K];
+        for (int q = 0; q < K; ++q) off[q] = __ldg(tab + (size_t)q * n_out + o);
+        double acc = 0.0;
+        for (uint32_t x = 0; x < cx; ++x) {
+            double val = 0.0;
 #pragma unroll
             for (int q = 0; q < K; ++q) {
-                t0[q] = *ptr[q];
-                t1[q] = *(ptr[q] + sxm[q]);
+                const uint32_t e = off[q] + x * op.sx[q];
+                const double t = ((amask >> q) & 1u) ? arena_smem[v.at(op.base[q] + e)] : __ldg(op.cpt[q] + e);
+                val = (q == 0) ? t : __dmul_rn(val, t);
             }
-            double v0 = t0[0], v1 = t1[0];
-#pragma unroll
-            for (int q = 1; q < K; ++q) {
-                v0 = __dmul_rn(v0, t0[q]);
-                v1 = __dmul_rn(v1, t1[q]);
-            }
-            acc = __dadd_rn(v0, v1);
-        } else {
-            acc = 0.0;
-            for (uint32_t x = 0; x < cx; ++x) {
-                double v = *(ptr[0] + (size_t)x * sxm[0]);
-#pragma unroll
-                for (int q = 1; q < K; ++q) v = __dmul_rn(v, *(ptr[q] + (size_t)x * sxm[q]));
-                acc = (x == 0) ? v : __dadd_rn(acc, v);
-            }
+            acc = (x == 0) ? val : __dadd_rn(acc, val);
         }
-        if (store) dst[(uint64_t)o * dmul] = acc;
+        put<SPW>(v, d, o, acc);
         zacc = __dadd_rn(zacc, acc);
     }
     return zacc;
 }
 
-// operand records of one step, then its entries; returns the program counter after the step
-template <int K, int G>
-__device__ __forceinline__ uint32_t fused_step(const FusedLaunch &p, uint32_t pc, double *abase, uint32_t amul,
-                                               const uint8_t *ev, uint32_t n_out, uint32_t cx, uint32_t tab_off,
-                                               uint32_t lane, double *dst, uint64_t dmul, bool store, double &zacc)
+template <int K, int G, int SPW>
+__device__ __forceinline__ double entries_dispatch(const SetView<SPW> &v, const Operands &op, uint32_t amask, bool pairs,
+                                                   const uint32_t *tab, uint32_t n_out, uint32_t cx, uint32_t lane, const Dest &d)
 {
-    const double *src[K];
-    uint32_t mul[K], sxm[K];
-#pragma unroll
-    for (int q = 0; q < K; ++q) {
-        const uint4 r = ldg4(p.prog + pc);
-        pc += kFusedOperandWords;
-        const uint32_t kind = r.x & 0xffu, nobs = r.x >> 8;
-        if (kind == 0) {
-            src[q] = abase + (size_t)r.y * amul;
-            mul[q] = amul;
-        } else {
-            uint32_t e = 0;
-            for (uint32_t j = 0; j < nobs; j += 2) {
-                const uint4 ob = ldg4(p.prog + pc);
-                pc += 4;
-                e += ob.x * ev[ob.y];
-                if (j + 1 < nobs) e += ob.z * ev[ob.w];
-            }
-            src[q] = reinterpret_cast<const double *>(((uint64_t)r.w << 32) | (uint64_t)r.y) + e;
-            mul[q] = 1;
+    if (pairs && K <= 3) {
+        // compile-time arena mask for the common operand counts
+        switch (amask) {
+        case 0: return entries_pairs<K, 0u, G, SPW>(v, op, tab, n_out, lane, d);
+        case 1: return entries_pairs<K, 1u, G, SPW>(v, op, tab, n_out, lane, d);
+        case 2: if (K >= 2) return entries_pairs<K, (K >= 2 ? 2u : 0u), G, SPW>(v, op, tab, n_out, lane, d); break;
+        case 3: if (K >= 2) return entries_pairs<K, (K >= 2 ? 3u : 0u), G, SPW>(v, op, tab, n_out, lane, d); break;
+        case 4: if (K >= 3) return entries_pairs<K, (K >= 3 ? 4u : 0u), G, SPW>(v, op, tab, n_out, lane, d); break;
+        case 5: if (K >= 3) return entries_pairs<K, (K >= 3 ? 5u : 0u), G, SPW>(v, op, tab, n_out, lane, d); break;
+        case 6: if (K >= 3) return entries_pairs<K, (K >= 3 ? 6u : 0u), G, SPW>(v, op, tab, n_out, lane, d); break;
+        case 7: if (K >= 3) return entries_pairs<K, (K >= 3 ? 7u : 0u), G, SPW>(v, op, tab, n_out, lane, d); break;
+        default: break;
         }
-        sxm[q] = r.z * mul[q];
     }
-    const uint32_t *tab = p.offtab + tab_off;
-    if (cx == 2) zacc = fused_entries<K, 2, G>(src, mul, sxm, tab, n_out, cx, lane, dst, dmul, store);
-    else if (cx == 1) zacc = fused_entries<K, 1, G>(src, mul, sxm, tab, n_out, cx, lane, dst, dmul, store);
-    else zacc = fused_entries<K, 0, G>(src, mul, sxm, tab, n_out, cx, lane, dst, dmul, store);
-    return pc;
+    return entries_any<K, G, SPW>(v, op, amask, tab, n_out, cx, lane, d);
 }
 
 template <int G>
 __global__ void __launch_bounds__(kFusedThreads) ve_fused(const __grid_constant__ FusedLaunch p)
 {
-    extern __shared__ double arena_smem[];
     constexpr int SPW = G >= 32 ? 1 : 32 / G;       // sets per warp, interleaved in the warp's slice of the arena
     constexpr int SPC = kFusedThreads / G;          // sets per CTA
     __shared__ double s_red[kFusedThreads / 32];
-    const uint32_t lane = threadIdx.x % G;
-    const uint32_t set_in_cta = threadIdx.x / G;
-    double *abase;
-    if (G < 32) abase = arena_smem + (size_t)(threadIdx.x / 32) * SPW * p.arena + (set_in_cta % SPW);
-    else abase = arena_smem + (size_t)set_in_cta * p.arena;
-    constexpr uint32_t amul = SPW;
+    const uint32_t tw = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t lane, set_in_cta;
+    SetView<SPW> v;
+    if (G < 32) {
+        lane = tw / SPW;
+        set_in_cta = warp * SPW + (tw % SPW);
+        v.wbase = warp * SPW * p.arena + 2u * (tw % SPW);
+    } else if (G == 32) {
+        lane = tw;
+        set_in_cta = warp;
+        v.wbase = warp * p.arena;
+    } else {
+        lane = threadIdx.x;
+        set_in_cta = 0;
+        v.wbase = 0;
+    }
     const uint32_t n_groups = (p.nb + SPC - 1) / SPC;
     for (uint32_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
         uint32_t b = grp * SPC + set_in_cta;
@@ -138,41 +200,70 @@ __global__ void __launch_bounds__(kFusedThreads) ve_fused(const __grid_constant_
         for (uint32_t s = 0; s < p.n_steps; ++s) {
             const uint4 h0 = ldg4(p.prog + pc), h1 = ldg4(p.prog + pc + 4);
             pc += kFusedHeaderWords;
-            const uint32_t n_out = h0.x, cx = h0.y, k = h0.z & 0xffu, flags = h0.z >> 8, out_off = h0.w, tab_off = h1.x;
-            double *dst;
-            uint64_t dmul;
-            bool store = true;
+            const uint32_t n_out = h0.x, cx = h0.y, k = h0.z & 0xffu, flags = h0.z >> 8, tab_off = h1.x;
+            Dest d;
+            d.out_off = h0.w;
+            d.store = live;
             if (flags & kFusedToResult) {
-                dst = p.result + ((uint64_t)out_off * p.nb + b);
-                dmul = p.nb;
-                store = live;
+                d.result = p.result + ((uint64_t)h0.w * p.nb + b);
+                d.stride = p.nb;
             } else {
-                dst = abase + (size_t)out_off * amul;
-                dmul = amul;
+                d.result = nullptr;
+                d.stride = 0;
             }
-            double zacc = 0.0;
+            // operand records (the k of a step is uniform over the grid)
+            Operands op;
+            uint32_t amask = 0;
+#pragma unroll
+            for (int q = 0; q < kMaxK; ++q) {
+                if (q < (int)k) {
+                    const uint4 r = ldg4(p.prog + pc);
+                    pc += kFusedOperandWords;
+                    op.sx[q] = r.z;
+                    if ((r.x & 0xffu) == 0) {
+                        op.base[q] = r.y;
+                        op.cpt[q] = nullptr;
+                        amask |= 1u << q;
+                    } else {
+                        const uint32_t nobs = r.x >> 8;
+                        uint32_t e = 0;
+                        for (uint32_t j = 0; j < nobs; j += 2) {
+                            const uint4 ob = ldg4(p.prog + pc);
+                            pc += 4;
+                            e += ob.x * ev[ob.y];
+                            if (j + 1 < nobs) e += ob.z * ev[ob.w];
+                        }
+                        op.base[q] = 0;
+                        op.cpt[q] = reinterpret_cast<const double *>(((uint64_t)r.w << 32) | (uint64_t)r.y) + e;
+                    }
+                }
+            }
+            const uint32_t *tab = p.offtab + tab_off;
+            const bool pairs = (flags & kFusedPairs) != 0;
+            double zacc;
             switch (k) {
-            case 1: pc = fused_step<1, G>(p, pc, abase, amul, ev, n_out, cx, tab_off, lane, dst, dmul, store, zacc); break;
-            case 2: pc = fused_step<2, G>(p, pc, abase, amul, ev, n_out, cx, tab_off, lane, dst, dmul, store, zacc); break;
-            case 3: pc = fused_step<3, G>(p, pc, abase, amul, ev, n_out, cx, tab_off, lane, dst, dmul, store, zacc); break;
-            case 4: pc = fused_step<4, G>(p, pc, abase, amul, ev, n_out, cx, tab_off, lane, dst, dmul, store, zacc); break;
-            case 5: pc = fused_step<5, G>(p, pc, abase, amul, ev, n_out, cx, tab_off, lane, dst, dmul, store, zacc); break;
-            default: pc = fused_step<6, G>(p, pc, abase, amul, ev, n_out, cx, tab_off, lane, dst, dmul, store, zacc); break;
+            case 1: zacc = entries_dispatch<1, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
+            case 2: zacc = entries_dispatch<2, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
+            case 3: zacc = entries_dispatch<3, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
+            case 4: zacc = entries_dispatch<4, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
+            case 5: zacc = entries_dispatch<5, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
+            default: zacc = entries_dispatch<6, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
             }
             if ((flags & kFusedWantZ) && p.z) {      // uniform over the grid; only single queries ask for it
-                double v = zacc;
+                double z = zacc;
                 if (G <= 32) {
+                    // the lanes of a set are the threads l * SPW + s of the warp
 #pragma unroll
-                    for (int o = (G < 32 ? G : 32) / 2; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+                    for (int o = 16; o >= SPW; o >>= 1) z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, o));
                 } else {
-                    v = warp_sum(v);
-                    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+                    z = warp_sum(z);
+                    if (tw == 0) s_red[warp] = z;
                     __syncthreads();
-                    v = 0.0;
+                    z = 0.0;
 #pragma unroll
-                    for (int i = 0; i < kFusedThreads / 32; ++i) v = __dadd_rn(v, s_red[i]);
+                    for (int i = 0; i < kFusedThreads / 32; ++i) z = __dadd_rn(z, s_red[i]);
                 }
-                if (lane == 0 && live) p.z[b] = v;
+                if (lane == 0 && live) p.z[b] = z;
             }
             group_sync<G>();     // the step's output is complete, and its operands are dead, before the next step
         }
@@ -183,7 +274,8 @@ bool fused_valid_g(int G) { return G == 8 || G == 16 || G == 32 || G == 128; }
 
 size_t fused_smem_bytes(int G, uint32_t arena)
 {
-    return (size_t)(kFusedThreads / G) * (arena ? arena : 1) * sizeof(double);
+    const uint32_t even = (arena + 1u) & ~1u;      // pairs of doubles stay together
+    return (size_t)(kFusedThreads / G) * (even ? even : 2) * sizeof(double);
 }
 
 typedef void (*fused_fn)(const FusedLaunch);
@@ -198,6 +290,7 @@ int fused_launch(bnpp_ctx *ctx, int G, const FusedLaunch &p)
     case 128: fn = ve_fused<128>; break;
     default: return fail(ctx, BNPP_EINVAL, "fused VE: lanes per set must be 8, 16, 32 or 128");
     }
+    if (p.arena & 1u) return fail(ctx, BNPP_EINVAL, "fused VE: the arena of a set must be an even number of doubles");
     const size_t smem = fused_smem_bytes(G, p.arena);
     static std::map<const void *, size_t> granted;      // dynamic shared memory opted into, per variant
     size_t &have = granted[reinterpret_cast<const void *>(fn)];
@@ -208,10 +301,8 @@ int fused_launch(bnpp_ctx *ctx, int G, const FusedLaunch &p)
     int per_sm = 0;
     BNPP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kFusedThreads, smem));
     if (per_sm < 1) return fail(ctx, BNPP_ETOOBIG, "fused VE: the arena of one CTA does not fit in shared memory");
-    // leave part of the SM's 256 KB to L1: the program, the offset tables and the CPTs are read through it
-    int cap = 6;
-    if (const char *e = getenv("BNPP_FUSED_CTAS_PER_SM")) cap = atoi(e) > 0 ? atoi(e) : cap;
-    if (per_sm > cap) per_sm = cap;
+    if (const char *e = getenv("BNPP_FUSED_CTAS_PER_SM"))      // experiments: cap the resident CTAs per SM
+        if (atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e);
     const uint32_t spc = kFusedThreads / G;
     uint64_t blocks = ((uint64_t)p.nb + spc - 1) / spc;
     const uint64_t resident = (uint64_t)ctx->sm_count * per_sm;

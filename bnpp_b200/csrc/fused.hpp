@@ -33,6 +33,7 @@ constexpr int kFusedInlineEv = 256;     // single query: evidence values travel 
 // each CPT operand followed by its observed axes, (stride, evidence column) pairs padded to 4 words
 constexpr uint32_t kFusedToResult = 1u;     // flags
 constexpr uint32_t kFusedWantZ = 2u;
+constexpr uint32_t kFusedPairs = 4u;        // cx == 2 and every arena operand holds the eliminated variable at stride 1 on even offsets
 constexpr uint32_t kFusedHeaderWords = 8;
 constexpr uint32_t kFusedOperandWords = 4;
 
@@ -43,7 +44,7 @@ struct FusedLaunch {
     double *result;             // [result_size][nb], batch fastest
     double *z;                  // nb == 1: partition of the result step (may be nullptr)
     uint32_t nb, n_obs, n_steps;
-    uint32_t arena;             // doubles of shared memory per evidence set
+    uint32_t arena;             // doubles of shared memory per evidence set (even)
     uint8_t ev_inline[kFusedInlineEv];
 };
 

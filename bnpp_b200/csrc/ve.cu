@@ -476,6 +476,7 @@ void fused_build(bnpp_ve_plan *pl)
     std::vector<std::pair<uint64_t, uint64_t>> free_list;   // (offset, size)
     uint64_t top = 0, peak = 0;
     auto take = [&](uint64_t n) {
+        n = (n + 1) & ~1ull;      // tables start on even offsets: the kernel moves pairs of doubles
         for (size_t i = 0; i < free_list.size(); ++i)
             if (free_list[i].second >= n) {
                 const uint64_t off = free_list[i].first;
@@ -489,6 +490,7 @@ void fused_build(bnpp_ve_plan *pl)
         return off;
     };
     auto give = [&](uint64_t off, uint64_t n) {
+        n = (n + 1) & ~1ull;
         free_list.push_back({off, n});
         std::sort(free_list.begin(), free_list.end());
         for (size_t i = 0; i + 1 < free_list.size();)
@@ -570,9 +572,16 @@ void fused_build(bnpp_ve_plan *pl)
                 }
             }
         }
-        uint32_t flags = 0, out_off;
+        // the pair form: binary eliminated variable at stride 1 in every arena operand, on even offsets
+        bool pairs = cx == 2;
+        for (int q = 0; q < k && pairs; ++q) {
+            if (pl->f[st.operands[q]].src >= 0) continue;
+            pairs = sx[q] == 1;
+            for (uint64_t o = 0; o < n_out && pairs; ++o) pairs = (fp.offtab[tab_off + (size_t)q * n_out + o] & 1u) == 0;
+        }
+        uint32_t flags = pairs ? kFusedPairs : 0u, out_off;
         if (st.out == -2) {
-            flags = kFusedToResult | (st.want_z ? kFusedWantZ : 0u);
+            flags |= kFusedToResult | (st.want_z ? kFusedWantZ : 0u);
             if (st.roff >= (1ull << 32)) return;
             out_off = (uint32_t)st.roff;
         } else {
@@ -607,7 +616,7 @@ void fused_build(bnpp_ve_plan *pl)
     fp.n_steps = (uint32_t)ns;
     fp.total_union = 0;
     for (const PlanStep &st : pl->steps) fp.total_union += st.union_entries;
-    fp.arena = (uint32_t)std::max<uint64_t>(peak, 1);
+    fp.arena = (uint32_t)std::max<uint64_t>((peak + 1) & ~1ull, 2);
     fp.tables.assign(pl->n_inputs, nullptr);
     fp.ok = true;
 }
