@@ -98,9 +98,9 @@ def test_marginals_one_launch(ctx, golden_models):
 def test_result_table_one_launch(ctx, golden_models):
     """VE that keeps variables (query_ve's numerator, code/model.cpp:225-238): the result table and its
     partition from the fused launch"""
-    import torch
     for name in ["asia", "alarm", "child"]:
-        bn = load(ctx, golden_models[name]["uai"])
+        m = golden_models[name]
+        bn = load(ctx, m["uai"])
         keep = [1, 3]
         order, _ = bn.order([v for v in range(bn.nvars) if v not in keep], {}, "mf")
         p = bn.plan([], order)
@@ -114,7 +114,8 @@ def test_result_table_one_launch(ctx, golden_models):
         res_b = res_b.cpu().numpy()
         assert scope == keep
         assert np.array_equal(res_f[:-1], res_b[:-1]), name
-        assert math.isclose(res_f[-1], res_b[-1], rel_tol=1e-14) and math.isclose(res_f[-1], 1.0, rel_tol=REL)
+        want = [c["pr"] for c in m["pr"] if not c["evidence"]][0]       # sum of the joint marginal = P() of the reference
+        assert math.isclose(res_f[-1], res_b[-1], rel_tol=1e-14) and math.isclose(res_f[-1], want, rel_tol=REL)
         bn.close()
 
 
@@ -180,16 +181,32 @@ def test_batch_large_one_launch(ctx):
     bn.close()
 
 
-def test_evidence_values_move_only_base_offsets(ctx, golden_synth):
-    """one fused plan, other evidence values and other table addresses: the program is re-pointed, not rebuilt"""
+def test_other_tables_other_evidence_same_program(ctx, golden_synth):
+    """one fused plan serves other evidence values (base offsets) and other table addresses (the program is
+    re-pointed, not rebuilt): a second copy of the model with its first CPT doubled gives exactly 2 Z"""
+    import torch
+    from bnpp_b200 import model
+    from fused_interp import parse_uai
     rec = [r for r in golden_synth["batch"] if r["fixed_ids"] and r["N"] < 100][0]
     text = synth.random_bn_uai(rec["N"], rec["W"], rec["K"], rec["seed"])
     evs = synth.evidence_batch(rec["N"], rec["nobs"], rec["nsets"], seed=5, fixed_ids=True)
-    bn1, bn2 = load(ctx, text), load(ctx, text)                # same model at two addresses
-    for i, ev in enumerate(evs):
-        for bn in (bn1, bn2):
-            z, _ = bn.partition(ev, "mf")
-            assert math.isclose(z, rec["pr"][i], rel_tol=REL), i
-    assert len(bn1._plans) == 1
+    cards, scopes, tables = parse_uai(text)
+    bn1 = model.BN(ctx, cards, list(zip(scopes, tables)))
+    bn2 = model.BN(ctx, cards, list(zip(scopes, [tables[0] * 2.0] + tables[1:])))
+    observed = sorted(evs[0])
+    order, _ = bn1.order([v for v in range(bn1.nvars) if v not in evs[0]], evs[0], "mf")
+    p = bn1.plan(observed, order)
+    assert p.fused_info(1)[0] > 0
+    with torch.cuda.stream(ctx.torch_stream):
+        res = torch.zeros(2, dtype=torch.float64, device="cuda")
+    for i, ev in enumerate(evs[:8]):
+        got = []
+        for bn in (bn1, bn2, bn1):
+            p.run(bn.table_ptrs, [ev[v] for v in observed], res.data_ptr(), res.data_ptr() + 8)
+            ctx.sync()
+            got.append(res.cpu().tolist())
+        assert math.isclose(got[0][0], rec["pr"][i], rel_tol=REL), i
+        assert got[0][0] == got[0][1] and got[2] == got[0]
+        assert got[1][0] == 2.0 * got[0][0], i
     bn1.close()
     bn2.close()
