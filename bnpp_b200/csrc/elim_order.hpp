@@ -11,6 +11,9 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <functional>
+#include <queue>
+#include <tuple>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -201,6 +204,8 @@ public:
         bits_.assign((size_t)n_ * words_, 0);
         present_.assign(n_, 0);
         deg_.assign(n_, 0);
+        lo_.assign(n_, words_);
+        hi_.assign(n_, 0);
         for (const auto &node : g.adjacency()) {
             present_[node.first] = 1;
             ++alive_;
@@ -211,33 +216,123 @@ public:
         dirty_.assign(n_, 1);
     }
 
+    // The same graph straight from the factor scopes (no hash containers): nodes = every scope
+    // variable, edges = the pairs of each scope (code/graph.cpp:11-34).
+    FastOrderer(const std::vector<std::vector<unsigned>> &scopes, const std::vector<unsigned> &card) : card_(card)
+    {
+        unsigned maxid = 0;
+        bool any = false;
+        for (const auto &sc : scopes)
+            for (unsigned v : sc) {
+                maxid = std::max(maxid, v);
+                any = true;
+            }
+        n_ = any ? maxid + 1 : 0;
+        words_ = (n_ + 63) / 64;
+        bits_.assign((size_t)n_ * words_, 0);
+        present_.assign(n_, 0);
+        deg_.assign(n_, 0);
+        lo_.assign(n_, words_);
+        hi_.assign(n_, 0);
+        for (const auto &sc : scopes) {
+            for (unsigned v : sc)
+                if (!present_[v]) {
+                    present_[v] = 1;
+                    ++alive_;
+                }
+            for (size_t i = 0; i + 1 < sc.size(); ++i)
+                for (size_t j = i + 1; j < sc.size(); ++j)
+                    if (sc[i] != sc[j]) {
+                        set(sc[i], sc[j]);
+                        set(sc[j], sc[i]);
+                    }
+        }
+        for (unsigned v = 0; v < n_; ++v) {
+            unsigned d = 0;
+            for (unsigned w = lo_[v]; w <= hi_[v] && w < words_; ++w) d += (unsigned)__builtin_popcountll(row(v)[w]);
+            deg_[v] = d;
+        }
+        score_.assign(n_, 0);
+        dirty_.assign(n_, 1);
+    }
+
+    // Every round of the reference scans ALL candidates in the iteration order of its
+    // std::unordered_set and keeps the first strict improvement of (score, then degree).
+    // Erasing from an unordered_set never reorders the remaining elements, so that order
+    // is fixed once the set is filled: `seq`.  The scan's winner is then the minimum of
+    // (score, degree, position in seq) -- kept in an ordered set whose keys are refreshed
+    // only for the nodes an elimination touched, instead of O(candidates) work per round.
+    // The one case where the scan is NOT that minimum -- plain min-fill seeds its best
+    // score with |nodes|+1 (code/graph.cpp:122-153), so when no candidate scores below
+    // the seed the first candidate survives unless a later one ties the seed with a smaller
+    // degree -- falls back to the literal scan for that round.
     std::vector<unsigned> ordering(const std::vector<unsigned> &vars, Heuristic h, unsigned &width)
     {
         std::unordered_set<unsigned> cand;
         for (unsigned v : vars) cand.insert(v);
+        const std::vector<unsigned> seq(cand.begin(), cand.end());
+        const size_t m = seq.size();
         std::vector<unsigned> order;
-        order.reserve(vars.size());
+        order.reserve(m);
         width = 0;
         const bool weighted = (h == H_WEIGHTED_MIN_FILL);
-        while (!cand.empty()) {
-            unsigned best = *cand.begin();
-            if (h == H_MIN_DEGREE) {
-                unsigned best_deg = alive_ + 1;
-                for (unsigned id : cand) {
-                    const unsigned d = degree(id);
-                    if (d < best_deg) { best = id; best_deg = d; }
-                }
-            } else {
-                unsigned best_fill = weighted ? fill(best, true) : alive_ + 1;
-                for (unsigned id : cand) {
-                    const unsigned f = fill(id, weighted);
-                    if (f < best_fill || (f == best_fill && degree(id) < degree(best))) { best = id; best_fill = f; }
+        typedef std::tuple<unsigned, unsigned, unsigned> Key;      // (score, degree, position)
+        // a min-heap with lazy deletion: a refreshed key is pushed, its stale copy is skipped when it surfaces
+        std::priority_queue<Key, std::vector<Key>, std::greater<Key>> heap;
+        std::vector<Key> key(m);
+        std::vector<char> live(m, 1);
+        std::vector<int> pos_of(n_, -1);                            // candidates that are graph nodes
+        auto make_key = [&](unsigned pos) {
+            const unsigned id = seq[pos];
+            if (h == H_MIN_DEGREE) return Key(degree(id), 0u, pos);
+            return Key(fill(id, weighted), degree(id), pos);
+        };
+        for (unsigned pos = 0; pos < m; ++pos) {
+            if (seq[pos] < n_) pos_of[seq[pos]] = (int)pos;
+            key[pos] = make_key(pos);
+            heap.push(key[pos]);
+        }
+        touched_.clear();
+        size_t left = m;
+        while (left) {
+            for (unsigned id : touched_) {
+                const int pos = id < n_ ? pos_of[id] : -1;
+                if (pos < 0 || !live[pos]) continue;
+                const Key k = make_key((unsigned)pos);
+                if (k != key[pos]) {
+                    key[pos] = k;
+                    heap.push(k);
                 }
             }
+            touched_.clear();
+            while (!live[std::get<2>(heap.top())] || heap.top() != key[std::get<2>(heap.top())]) heap.pop();
+            unsigned best_pos = std::get<2>(heap.top());
+            if (h == H_MIN_FILL && std::get<0>(heap.top()) >= alive_ + 1) {
+                // the literal scan of code/graph.cpp:122-153
+                bool first = true;
+                unsigned best = 0, best_fill = alive_ + 1;
+                for (unsigned pos = 0; pos < m; ++pos) {
+                    if (!live[pos]) continue;
+                    const unsigned id = seq[pos];
+                    if (first) {
+                        best = id;
+                        best_pos = pos;
+                        first = false;
+                    }
+                    const unsigned f = fill(id, false);
+                    if (f < best_fill || (f == best_fill && degree(id) < degree(best))) {
+                        best = id;
+                        best_pos = pos;
+                        best_fill = f;
+                    }
+                }
+            }
+            const unsigned best = seq[best_pos];
             order.push_back(best);
+            live[best_pos] = 0;
+            --left;
             const unsigned d = eliminate(best);
             if (d > width) width = d;
-            cand.erase(best);
         }
         return order;
     }
@@ -245,15 +340,23 @@ public:
 private:
     uint64_t *row(unsigned a) { return &bits_[(size_t)a * words_]; }
     const uint64_t *row(unsigned a) const { return &bits_[(size_t)a * words_]; }
-    void set(unsigned a, unsigned b) { row(a)[b >> 6] |= 1ull << (b & 63); }
+    void set(unsigned a, unsigned b)
+    {
+        const unsigned w = b >> 6;
+        row(a)[w] |= 1ull << (b & 63);
+        if (w < lo_[a]) lo_[a] = w;
+        if (w > hi_[a]) hi_[a] = w;
+    }
     void clear(unsigned a, unsigned b) { row(a)[b >> 6] &= ~(1ull << (b & 63)); }
     bool test(unsigned a, unsigned b) const { return (row(a)[b >> 6] >> (b & 63)) & 1ull; }
     unsigned degree(unsigned id) const { return id < n_ ? deg_[id] : 0; }
 
+    // lo_/hi_: the words of a row that ever held a bit (rows of a sparse graph are mostly empty words)
     template <class F>
-    void for_each(const uint64_t *r, F f) const
+    void for_each(unsigned v, F f) const
     {
-        for (unsigned w = 0; w < words_; ++w) {
+        const uint64_t *r = row(v);
+        for (unsigned w = lo_[v]; w <= hi_[v] && w < words_; ++w) {
             uint64_t x = r[w];
             while (x) {
                 const unsigned b = (unsigned)__builtin_ctzll(x);
@@ -271,21 +374,23 @@ private:
         uint64_t s;
         if (!weighted) {
             uint64_t inside = 0;   // ordered pairs (a, b) of neighbours that are adjacent
-            for_each(nw, [&](unsigned a) {
+            for_each(id, [&](unsigned a) {
                 const uint64_t *na = row(a);
-                for (unsigned w = 0; w < words_; ++w) inside += (uint64_t)__builtin_popcountll(na[w] & nw[w]);
+                const unsigned w0 = std::max(lo_[a], lo_[id]), w1 = std::min(hi_[a], hi_[id]);
+                for (unsigned w = w0; w <= w1 && w < words_; ++w) inside += (uint64_t)__builtin_popcountll(na[w] & nw[w]);
             });
             const uint64_t d = deg_[id];
             s = d * (d - (d ? 1 : 0)) / 2 - inside / 2;
         } else {
             uint64_t sum = 0, sq = 0, inside = 0;
-            for_each(nw, [&](unsigned a) {
+            for_each(id, [&](unsigned a) {
                 const uint64_t ca = card_.at(a);
                 sum += ca;
                 sq += ca * ca;
                 const uint64_t *na = row(a);
                 uint64_t acc = 0;
-                for (unsigned w = 0; w < words_; ++w) {
+                const unsigned w0 = std::max(lo_[a], lo_[id]), w1 = std::min(hi_[a], hi_[id]);
+                for (unsigned w = w0; w <= w1 && w < words_; ++w) {
                     uint64_t x = na[w] & nw[w];
                     while (x) {
                         const unsigned b = (unsigned)__builtin_ctzll(x);
@@ -306,11 +411,12 @@ private:
     {
         if (v >= n_ || !present_[v]) return 0;
         std::vector<unsigned> nb;
-        for_each(row(v), [&](unsigned a) { nb.push_back(a); });
+        for_each(v, [&](unsigned a) { nb.push_back(a); });
         for (unsigned a : nb) {
             clear(a, v);
             --deg_[a];
             dirty_[a] = 1;
+            touched_.push_back(a);
         }
         for (size_t i = 0; i < nb.size(); ++i)
             for (size_t j = i + 1; j < nb.size(); ++j) {
@@ -318,11 +424,13 @@ private:
                 if (test(a, b)) continue;
                 // a new edge changes the fill-in of every common neighbour of its end points
                 const uint64_t *ra = row(a), *rb = row(b);
-                for (unsigned w = 0; w < words_; ++w) {
+                const unsigned w0 = std::max(lo_[a], lo_[b]), w1 = std::min(hi_[a], hi_[b]);
+                for (unsigned w = w0; w <= w1 && w < words_; ++w) {
                     uint64_t x = ra[w] & rb[w];
                     while (x) {
                         const unsigned c = (unsigned)__builtin_ctzll(x);
                         x &= x - 1;
+                        if (!dirty_[w * 64 + c]) touched_.push_back(w * 64 + c);
                         dirty_[w * 64 + c] = 1;
                     }
                 }
@@ -331,7 +439,7 @@ private:
                 ++deg_[a];
                 ++deg_[b];
             }
-        std::fill(row(v), row(v) + words_, 0);
+        if (lo_[v] <= hi_[v]) std::fill(row(v) + lo_[v], row(v) + std::min(hi_[v] + 1, words_), 0);
         deg_[v] = 0;
         present_[v] = 0;
         --alive_;
@@ -343,6 +451,8 @@ private:
     std::vector<uint64_t> bits_;
     std::vector<char> present_, dirty_;
     std::vector<unsigned> deg_, score_;
+    std::vector<unsigned> lo_, hi_;     // per row: first and last word that ever held a bit (lo > hi: none)
+    std::vector<unsigned> touched_;     // nodes whose score or degree the last elimination changed
 };
 
 }  // namespace bnpp

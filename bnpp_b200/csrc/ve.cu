@@ -52,6 +52,33 @@ struct PlanStep {
     uint64_t union_entries = 0, bytes = 0;
 };
 
+// variable id -> elimination time.  Ids are dense small integers in every UAI model: a flat
+// table (planning a 1000-variable network does ~10^5 lookups); stray large ids fall back to a map.
+class RankMap {
+public:
+    bool count(uint32_t v) const { return v < kDense ? (v < has_.size() && has_[v]) : sparse_.count(v) != 0; }
+    uint64_t at(uint32_t v) const { return v < kDense ? (v < val_.size() ? val_[v] : UINT64_MAX) : sparse_.at(v); }
+    void set(uint32_t v, uint64_t r)
+    {
+        if (v >= kDense) {
+            sparse_[v] = r;
+            return;
+        }
+        if (v >= has_.size()) {
+            has_.resize((size_t)v + 64, 0);
+            val_.resize((size_t)v + 64, 0);
+        }
+        has_[v] = 1;
+        val_[v] = r;
+    }
+
+private:
+    static constexpr uint32_t kDense = 1u << 22;
+    std::vector<char> has_;
+    std::vector<uint64_t> val_;
+    std::map<uint32_t, uint64_t> sparse_;
+};
+
 // K9: the plan compiled into the step program of fused.hpp (one launch for the whole plan)
 struct FusedProgram {
     bool built = false, ok = false;
@@ -121,7 +148,7 @@ uint64_t table_size(const std::vector<uint32_t> &card)
 
 // one fused launch description: product of `ops`, optionally eliminating `elim`, output
 // in canonical order (descending rank => the lowest-rank variable is the fastest axis)
-int add_step(bnpp_ve_plan *pl, std::vector<int> ops, int64_t elim, const std::map<uint32_t, uint64_t> &rank, bool to_result,
+int add_step(bnpp_ve_plan *pl, std::vector<int> ops, int64_t elim, const RankMap &rank, bool to_result,
              uint64_t roff = 0, bool want_z = true)
 {
     std::vector<std::pair<uint64_t, std::pair<uint32_t, uint32_t>>> u;   // (rank, (var, card))
@@ -161,20 +188,25 @@ int add_step(bnpp_ve_plan *pl, std::vector<int> ops, int64_t elim, const std::ma
         pl->result_card = out.card;
         pl->result_size = out.size;
     } else {
-        pl->f.push_back(out);
+        pl->f.push_back(std::move(out));
         st.out = (int)pl->f.size() - 1;
     }
-    pl->steps.push_back(st);
-    return st.out;
+    const int out_id = st.out;
+    pl->steps.push_back(std::move(st));
+    return out_id;
 }
 
 uint64_t union_size(const bnpp_ve_plan *pl, const std::vector<int> &ops)
 {
-    std::map<uint32_t, uint32_t> u;
-    for (int id : ops)
-        for (size_t i = 0; i < pl->f[id].var.size(); ++i) u[pl->f[id].var[i]] = pl->f[id].card[i];
+    std::vector<uint32_t> seen;
     uint64_t n = 1;
-    for (auto &e : u) n *= e.second;
+    for (int id : ops)
+        for (size_t i = 0; i < pl->f[id].var.size(); ++i) {
+            const uint32_t v = pl->f[id].var[i];
+            if (std::find(seen.begin(), seen.end(), v) != seen.end()) continue;
+            seen.push_back(v);
+            n *= pl->f[id].card[i];
+        }
     return n;
 }
 
@@ -183,7 +215,7 @@ uint64_t union_size(const bnpp_ve_plan *pl, const std::vector<int> &ops)
 // one small (L2-resident) table first costs a negligible launch and leaves the streaming
 // kernel with the wide operand(s) plus one small one (K <= 3: the `canon` variant).
 constexpr uint64_t kWideEntries = 1ull << 20;
-void fold_small(bnpp_ve_plan *pl, std::vector<int> &ops, const std::map<uint32_t, uint64_t> &rank)
+void fold_small(bnpp_ve_plan *pl, std::vector<int> &ops, const RankMap &rank)
 {
     if (ops.empty()) return;
     const uint64_t whole = union_size(pl, ops);          // entries the bucket's launch iterates over
@@ -221,7 +253,7 @@ void fold_small(bnpp_ve_plan *pl, std::vector<int> &ops, const std::map<uint32_t
 }
 
 // the kernel takes at most BNPP_MAX_OPERANDS tables: fold the smallest ones first
-void shrink(bnpp_ve_plan *pl, std::vector<int> &ops, const std::map<uint32_t, uint64_t> &rank)
+void shrink(bnpp_ve_plan *pl, std::vector<int> &ops, const RankMap &rank)
 {
     while ((int)ops.size() > kMaxK) {
         std::stable_sort(ops.begin(), ops.end(), [pl](int a, int b) { return pl->f[a].size < pl->f[b].size; });
@@ -236,7 +268,7 @@ void shrink(bnpp_ve_plan *pl, std::vector<int> &ops, const std::map<uint32_t, ui
 
 // the input tables as evidence-reduced views (code/domain.cpp:74-90: free axes keep their order)
 int add_inputs(bnpp_ve_plan *pl, int nfac, const bnpp_scope *scopes, const std::map<uint32_t, int> &obs_index,
-               std::map<uint32_t, uint64_t> &rank)
+               RankMap &rank)
 {
     for (int q = 0; q < nfac; ++q) {
         const bnpp_scope &s = scopes[q];
@@ -258,7 +290,7 @@ int add_inputs(bnpp_ve_plan *pl, int nfac, const bnpp_scope *scopes, const std::
             pf.var.push_back(s.var_id[i]);
             pf.card.push_back(s.card[i]);
             pf.stride.push_back(st[i]);
-            if (!rank.count(s.var_id[i])) rank[s.var_id[i]] = (1ull << 40) + (0xffffffffull - s.var_id[i]);   // kept: ascending id, most significant first
+            if (!rank.count(s.var_id[i])) rank.set(s.var_id[i], (1ull << 40) + (0xffffffffull - s.var_id[i]));   // kept: ascending id, most significant first
         }
         pf.size = table_size(pf.card);
         pl->f.push_back(pf);
@@ -268,7 +300,7 @@ int add_inputs(bnpp_ve_plan *pl, int nfac, const bnpp_scope *scopes, const std::
 
 // product of `ops`, then every variable outside `keep` summed out one fused launch at a time
 // (the first launch also does the product); -1 when there is nothing to multiply
-int chain(bnpp_ve_plan *pl, std::vector<int> ops, const std::vector<uint32_t> &keep, const std::map<uint32_t, uint64_t> &rank,
+int chain(bnpp_ve_plan *pl, std::vector<int> ops, const std::vector<uint32_t> &keep, const RankMap &rank,
           bool to_result, uint64_t roff)
 {
     if (ops.empty()) return -1;
@@ -339,8 +371,8 @@ void build_exec(bnpp_ve_plan *pl)
 
     // launches are resolved lazily, step by step, during the first run (plan_step): the GPU already
     // executes the early buckets while the host is still resolving the later ones
-    pl->exec.assign(pl->steps.size(), LaunchDesc());
-    pl->exec_planned.assign(pl->steps.size(), 0);
+    // (the descriptors themselves -- 4 KB each -- are allocated by the first launch-per-bucket run: a plan that
+    // runs fused never needs them)
     pl->exec_ok = true;
 }
 
@@ -558,17 +590,23 @@ void fused_build(bnpp_ve_plan *pl)
         const uint32_t tab_off = (uint32_t)fp.offtab.size();
         fp.offtab.resize(fp.offtab.size() + (size_t)k * n_out, 0);
         {
+            // odometer over the output axes, the operand offsets updated incrementally
             std::vector<uint32_t> digit(wr, 0);
+            uint64_t cur[kMaxK] = {0};
+            for (int q = 0; q < k; ++q) {
+                uint64_t top = 0;
+                for (int a = 0; a < wr; ++a) top += (uint64_t)(ocard[a] - 1) * axs[q][a];
+                if (top >= (1ull << 32)) return;
+            }
             for (uint64_t o = 0; o < n_out; ++o) {
-                for (int q = 0; q < k; ++q) {
-                    uint64_t off = 0;
-                    for (int a = 0; a < wr; ++a) off += (uint64_t)digit[a] * axs[q][a];
-                    if (off >= (1ull << 32)) return;
-                    fp.offtab[tab_off + (size_t)q * n_out + o] = (uint32_t)off;
-                }
+                for (int q = 0; q < k; ++q) fp.offtab[tab_off + (size_t)q * n_out + o] = (uint32_t)cur[q];
                 for (int a = wr - 1; a >= 0; --a) {
-                    if (++digit[a] < ocard[a]) break;
+                    if (++digit[a] < ocard[a]) {
+                        for (int q = 0; q < k; ++q) cur[q] += axs[q][a];
+                        break;
+                    }
                     digit[a] = 0;
+                    for (int q = 0; q < k; ++q) cur[q] -= (uint64_t)(ocard[a] - 1) * axs[q][a];
                 }
             }
         }
@@ -715,13 +753,13 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
 
     std::map<uint32_t, int> obs_index;
     for (int i = 0; i < n_obs; ++i) obs_index[obs_var[i]] = i;
-    std::map<uint32_t, uint64_t> rank;           // elimination time; kept variables after all eliminated ones
+    RankMap rank;           // elimination time; kept variables after all eliminated ones
     for (int i = 0; i < n_order; ++i) {
         if (rank.count(order[i]) || obs_index.count(order[i])) {
             delete pl;
             return fail(ctx, BNPP_EINVAL, "elimination order repeats a variable or names an observed one");
         }
-        rank[order[i]] = (uint64_t)i;
+        rank.set(order[i], (uint64_t)i);
     }
 
     if (int rc = add_inputs(pl, nfac, scopes, obs_index, rank)) {
@@ -796,13 +834,13 @@ int bnpp_mar_plan_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfa
     pl->is_mar = true;
     std::map<uint32_t, int> obs_index;
     for (int i = 0; i < n_obs; ++i) obs_index[obs_var[i]] = i;
-    std::map<uint32_t, uint64_t> rank;
+    RankMap rank;
     for (int i = 0; i < n_order; ++i) {
         if (rank.count(order[i]) || obs_index.count(order[i])) {
             delete pl;
             return fail(ctx, BNPP_EINVAL, "elimination order repeats a variable or names an observed one");
         }
-        rank[order[i]] = (uint64_t)i;
+        rank.set(order[i], (uint64_t)i);
     }
     if (int rc = add_inputs(pl, nfac, scopes, obs_index, rank)) {
         delete pl;
@@ -1135,6 +1173,10 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             rc = bnpp_alloc(ctx, pl->arena_doubles, &pl->arena);
             if (rc != BNPP_OK) return rc;
         }
+        if (pl->exec.size() != pl->steps.size()) {
+            pl->exec.assign(pl->steps.size(), LaunchDesc());
+            pl->exec_planned.assign(pl->steps.size(), 0);
+        }
         for (size_t i = 0; i < pl->f.size(); ++i)
             if (pl->f[i].src < 0) ptr[i] = pl->arena + pl->arena_off[i];
         const bool graphed = pl->use_graph && !pl->profiling && pl->steps.size() > 1 && pl->runs >= 1;
@@ -1347,14 +1389,13 @@ int bnpp_elim_order(int nvars, const uint32_t *card, int nfac, const bnpp_scope 
             if (v >= (uint32_t)nvars || !observed[v]) sc[f].push_back(v);
         }
     std::vector<unsigned> c(card, card + nvars);
-    InteractionGraph g(sc, c);
     std::vector<unsigned> v;
     for (int i = 0; i < n_vars_to_order; ++i)
         if (vars[i] >= (uint32_t)nvars || !observed[vars[i]]) v.push_back(vars[i]);
     unsigned width = 0;
     std::vector<unsigned> order;
-    if (reference_containers) order = g.ordering(v, (Heuristic)heuristic, width);
-    else order = FastOrderer(g).ordering(v, (Heuristic)heuristic, width);
+    if (reference_containers) order = InteractionGraph(sc, c).ordering(v, (Heuristic)heuristic, width);
+    else order = FastOrderer(sc, c).ordering(v, (Heuristic)heuristic, width);
     for (size_t i = 0; i < order.size(); ++i) order_out[i] = order[i];
     if (n_order_out) *n_order_out = (uint32_t)order.size();
     if (width_out) *width_out = width;

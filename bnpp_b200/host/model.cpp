@@ -112,15 +112,14 @@ Factor Model::eliminate(const std::vector<const Variable*> &variables, const std
         }
         std::vector<unsigned> card;
         for (const Variable *pv : _variables) card.push_back(pv->size());
-        bnpp::InteractionGraph g(scopes, card);
         bnpp::Heuristic h = bnpp::H_MIN_FILL;
         if (options["min-degree"]) h = bnpp::H_MIN_DEGREE;
         else if (options["weighted-min-fill"]) h = bnpp::H_WEIGHTED_MIN_FILL;
         unsigned width = 0;
-        ids = bnpp::FastOrderer(g).ordering(ids, h, width);
+        ids = bnpp::FastOrderer(scopes, card).ordering(ids, h, width);
         if (options["verbose"]) {
             // same (mis)label as the reference (code/model.cpp:371-379, SURVEY A.2 iii)
-            std::cout << ">> Original elimination order (width = " << g.order_width(ids) << ")" << std::endl << "  ";
+            std::cout << ">> Original elimination order (width = " << bnpp::InteractionGraph(scopes, card).order_width(ids) << ")" << std::endl << "  ";
             for (unsigned id : ids) std::cout << " " << id;
             std::cout << std::endl << std::endl;
         }
@@ -199,12 +198,11 @@ std::vector<const Factor*> Model::marginals_ve(const std::unordered_map<unsigned
                 if (evidence.find(id) == evidence.end()) sc.push_back(id);
             scopes.push_back(sc);
         }
-        bnpp::InteractionGraph g(scopes, card);
         bnpp::Heuristic h = bnpp::H_MIN_FILL;
         if (options["min-degree"]) h = bnpp::H_MIN_DEGREE;
         else if (options["weighted-min-fill"]) h = bnpp::H_WEIGHTED_MIN_FILL;
         unsigned width = 0;
-        ids = bnpp::FastOrderer(g).ordering(ids, h, width);
+        ids = bnpp::FastOrderer(scopes, card).ordering(ids, h, width);
     }
     std::vector<bnpp_scope> scopes(factors.size());
     std::vector<const double*> tables(factors.size());
