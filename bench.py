@@ -185,6 +185,57 @@ def union_entries(scopes, order):
     return total
 
 
+def config5_leg(ctx, steps, warmup):
+    """The other half of BASELINE.json's metric -- VE PR queries/sec -- on config 5: 65 536 evidence sets on
+    the 500-variable BN, PR per set, one GPU (tools/batch_bench.py is the multi-GPU version).  Device-timed
+    with the evidence resident, and end to end from pinned host evidence (ordering, planning, H2D, the
+    launch, D2H of every Z) with nothing cached."""
+    import torch
+    from bnpp_b200 import model, synth
+    N, W, K, seed, nobs, nsets = 500, 6, 3, 11, 20, 65536
+    _, bn = model.from_uai_text(ctx, synth.random_bn_uai(N, W, K, seed))
+    evs = synth.evidence_batch(N, nobs, nsets, seed=5, fixed_ids=True)
+    observed = sorted(evs[0])
+    host = torch.tensor([[ev[v] for v in observed] for ev in evs], dtype=torch.uint8).pin_memory()
+    dev = host.cuda()
+    s = ctx.torch_stream
+    for _ in range(max(3, warmup)):
+        z = bn.partition_batch(observed, dev, "mf")
+    ctx.sync()
+    torch.cuda.synchronize()
+    l0 = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    for _ in range(steps):
+        z = bn.partition_batch(observed, dev, "mf")
+    e1.record(s)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = (ctx.launches - l0) // steps
+    plan = list(bn._plans.values())[0]
+    lanes, arena, n_steps = plan.fused_info(nsets)
+    union_entries = plan.union_entries
+    per_iter = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        bn.drop_plans()
+        z = bn.partition_batch(observed, None, "mf", host_values=host)
+        with torch.cuda.stream(s):
+            zh = z.to("cpu", non_blocking=False)
+        per_iter.append((time.perf_counter() - t0) * 1e3)
+    e2e_ms = sum(per_iter) / len(per_iter)
+    bn.close()
+    return {"metric": "VE PR queries/sec", "value": nsets / ms * 1e3, "unit": "queries/s", "ms_per_batch": ms,
+            "config": {"workload": "config 5: %d evidence sets, synthetic BN N=%d W=%d K=%d seed=%d, %d observed ids fixed, "
+                                   "PR per set via VE (min-fill)" % (nsets, N, W, K, seed, nobs)},
+            "e2e": {"value": nsets / e2e_ms * 1e3, "unit": "queries/s", "ms_per_batch": e2e_ms,
+                    "h2d_bytes_per_step": host.numel(), "d2h_bytes_per_step": 8 * nsets},
+            "gpu_launches_per_batch": launches, "union_entries_per_s": union_entries * nsets / ms * 1e3,
+            "kernel": ("ve_fused: one launch, %d lanes per evidence set, %d doubles of shared memory per set, %d steps"
+                       % (lanes, arena, n_steps)) if lanes else "contract_batched: one launch per bucket",
+            "sample_Z": zh[:2].tolist()}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,6 +243,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the PR-queries/sec leg (config 5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -362,6 +414,13 @@ def main():
                                              "frac": big_bytes / big_ms / 1e6 / peak if big_ms else None,
                                              "share_of_step_ms": big_ms / all_ms if all_ms else None}}
 
+    config5 = None
+    if n_gpus == 1 and not args.no_config5:
+        try:
+            config5 = config5_leg(ctx, args.steps, args.warmup)
+        except Exception as e:      # the headline line must not depend on the auxiliary leg
+            config5 = {"error": "%s: %s" % (type(e).__name__, e)}
+
     cb = None
     if not args.no_cpu_baseline:
         cb, _ = cpu_reference_leg(1)
@@ -379,7 +438,8 @@ def main():
                        "partition": z_total, "partition_e2e": z_e2e, "peak_intermediate_GB": plan.peak_bytes / 1e9},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bn.h2d_bytes, "d2h_bytes_per_step": 16,
                     "ms_per_step": e2e_s / args.steps * 1e3, "host_breakdown_ms": e2e_parts},
-            "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb}
+            "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cb,
+            "pr_queries": config5}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

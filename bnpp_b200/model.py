@@ -55,7 +55,7 @@ def _scopes(scope_list, cards):
     return arr, keep
 
 
-def elim_order(cards, scopes, variables, heuristic, reference_containers=False, observed=(), _arr=None):
+def elim_order(cards, scopes, variables, heuristic, reference_containers=False, observed=(), _arr=None, _cards=None):
     """Graph(...).ordering(variables) of code/graph.cpp:41-101 -> (order, width).  Host only.
     `scopes` are ORIGINAL factor scopes; `observed` variables are removed from them (and from
     `variables`) inside the library, as BN::partition does by conditioning (code/model.cpp:283-287).
@@ -63,7 +63,7 @@ def elim_order(cards, scopes, variables, heuristic, reference_containers=False, 
     L = capi.lib()
     _declare(L)
     arr = _arr if _arr is not None else _scopes(scopes, cards)[0]
-    c = capi._u32(cards)
+    c = _cards if _cards is not None else capi._u32(cards)
     v = capi._u32(variables)
     ob = capi._u32(list(observed))
     out = (ctypes.c_uint32 * max(1, len(variables)))()
@@ -232,6 +232,7 @@ class BN:
         self._batch_out = {}
         self.last_timing = {}
         self._scope_arr, self._scope_keep = _scopes(self.scopes, self.cards)   # the model's structure never changes
+        self._cards_arr = capi._u32(self.cards)
 
     @property
     def nvars(self):
@@ -249,7 +250,8 @@ class BN:
         """the order BN::variable_elimination uses (code/model.cpp:358-369)"""
         if heuristic is None:
             return [v for v in variables if v not in observed], None
-        return elim_order(self.cards, self.scopes, variables, heuristic, observed=sorted(observed), _arr=self._scope_arr)
+        return elim_order(self.cards, self.scopes, variables, heuristic, observed=sorted(observed), _arr=self._scope_arr,
+                          _cards=self._cards_arr)
 
     def plan(self, observed, order):
         key = (tuple(observed), tuple(order))
