@@ -1,7 +1,7 @@
 """The C++ host mirror (namespace bn: Factor / Domain / Graph / FactorGraph / BN / MN, the bn and
 mn CLIs) on top of the C ABI.
 
-`bnpp_b200/bin/harness` is oracle/ref_harness.cpp -- the very source that drives the UNMODIFIED
+`tests/bin/harness` (tests/harness/Makefile) is oracle/ref_harness.cpp -- the very source that drives the UNMODIFIED
 reference -- compiled against this repo's headers, so each test reads like a reference-side test:
 same commands, answers compared with the reference's (tests/golden, or oracle/_ref run side by side).
 """
@@ -23,7 +23,7 @@ REL = 1e-9
 
 
 def run_harness(script, exe=None):
-    exe = exe or os.path.join(BIN, "harness")
+    exe = exe or os.path.join(ROOT, "tests", "bin", "harness")
     p = subprocess.run([exe], input="\n".join(script) + "\n", capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-2000:]
     return [ln.split() for ln in p.stdout.splitlines() if ln.strip()]

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""`bn <model> -pr -mf` on every shipped Bayesian network: this build vs the unmodified reference
+"""Test infrastructure (it executes the reference under oracle/_ref).
+`bn <model> -pr -mf` on every shipped Bayesian network: this build vs the unmodified reference
 (oracle/_ref), partition line and the tools' own `Executed in` times.  Markdown table on stdout."""
 import glob
 import os
@@ -7,7 +8,7 @@ import re
 import subprocess
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF = os.path.join(ROOT, "oracle", "_ref")
 
 
