@@ -37,3 +37,17 @@ def test_no_cpu_fallback(tmp_path, golden_models):
     p = subprocess.run([os.path.join(BIN, "bn"), str(f), "-pr"], capture_output=True, text=True)
     assert p.returncode == 3
     assert "cannot create a CUDA context" in p.stderr and "Partition" not in p.stdout
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="this box has a GPU")
+def test_api_harness_links_and_has_no_cpu_fallback(tmp_path, golden_models):
+    """tests/bin/harness = the reference's own harness source compiled against the product's headers
+    (tests/harness/Makefile): it must find libbnpp_b200.so next to the package and refuse to compute without a GPU"""
+    exe = os.path.join(ROOT, "tests", "bin", "harness")
+    if not os.path.exists(exe):
+        pytest.skip("harness not built (run build())")
+    f = tmp_path / "asia.uai"
+    f.write_text(golden_models["asia"]["uai"])
+    p = subprocess.run([exe], input="model %s\npr\n" % f, capture_output=True, text=True)
+    assert p.returncode == 3, (p.returncode, p.stderr[-300:])
+    assert "cannot create a CUDA context" in p.stderr and "PR" not in p.stdout
