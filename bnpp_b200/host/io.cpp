@@ -1,4 +1,5 @@
 #include "io.hh"
+#include "uai_parse.hpp"
 
 #include <iostream>
 
@@ -29,9 +30,37 @@ double next_double(std::ifstream &in)
     return next_token(in, tok) ? std::stod(tok) : 0.0;
 }
 
+// Well-formed files: one read, tokens scanned in place (uai_parse.hpp).  false = "not sure": the caller
+// re-reads the file with the reference's token-at-a-time reader below.
+template <class M>
+bool load_fast(std::string &filename, M **model, const char *want, const char *other, int &rc)
+{
+    std::string buf;
+    uai::Parsed p;
+    if (!uai::slurp(filename, buf) || !uai::parse_model(buf.data(), buf.size(), p)) return false;
+    if (p.type == other) {
+        std::cerr << "Error: file " << filename << " is not a " << want << " net." << std::endl;
+        rc = -2;
+        return true;
+    }
+    std::vector<Variable*> variables;
+    std::vector<Factor*> factors;
+    for (unsigned id = 0; id < p.card.size(); ++id) variables.push_back(new Variable(id, p.card[id]));
+    for (size_t f = 0; f < p.scopes.size(); ++f) {
+        std::vector<const Variable*> scope;
+        for (unsigned id : p.scopes[f]) scope.push_back(variables[id]);
+        factors.push_back(new Factor(new Domain(scope), p.values[f], p.partition[f]));
+    }
+    if (p.type == want) *model = new M(filename, variables, factors);
+    rc = 0;
+    return true;
+}
+
 template <class M>
 int load(std::string &filename, M **model, const char *want, const char *other)
 {
+    int rc = 0;
+    if (load_fast(filename, model, want, other, rc)) return rc;
     std::ifstream in(filename);
     if (!in.is_open()) {
         std::cerr << "Error: couldn't read file " << filename << std::endl;

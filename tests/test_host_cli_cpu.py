@@ -51,3 +51,56 @@ def test_api_harness_links_and_has_no_cpu_fallback(tmp_path, golden_models):
     p = subprocess.run([exe], input="model %s\npr\n" % f, capture_output=True, text=True)
     assert p.returncode == 3, (p.returncode, p.stderr[-300:])
     assert "cannot create a CUDA context" in p.stderr and "PR" not in p.stdout
+
+
+def _check(paths):
+    exe = os.path.join(ROOT, "tests", "bin", "uai_parse_check")
+    if not os.path.exists(exe):
+        pytest.skip("uai_parse_check not built (run build())")
+    p = subprocess.run([exe] + [str(x) for x in paths], capture_output=True, text=True)
+    rows = {}
+    for line in p.stdout.splitlines():
+        f = line.split()
+        rows[os.path.basename(f[0])] = f[5]
+    return p.returncode, rows
+
+
+def test_fast_uai_reader_equals_reference_reader(tmp_path, golden_models):
+    """bnpp_b200/host/uai_parse.hpp (one read, tokens in place, from_chars) against a restatement of the reference's
+    reader (code/io.cpp:14-100): bit-identical values and partitions on every shipped network and on the
+    golden texts; anything unusual must make the fast reader step aside (FALLBACK), never differ"""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", "models", "*", "*.uai")))
+    for name, m in golden_models.items():
+        f = tmp_path / (name + ".golden.uai")
+        f.write_text(m["uai"])
+        files.append(str(f))
+    rc, rows = _check(files)
+    assert rc == 0
+    assert len(rows) >= len(golden_models) and all(v == "SAME" for v in rows.values()), rows
+    body = "2\n2 3\n2\n1 0\n2 0 1\n2 0.25 0.75\n6 1 2 3 4 5 6\n"
+    odd = {
+        "comments.uai": "BAYES # a comment\n# whole line\n2 #cards follow\n2 3\n2\n1 0\n2 0 1\n2 0.25 0.75 # tail\n6 1 2 3 4 5 6 #end",
+        "crlf.uai": ("MARKOV\n" + body).replace("\n", "\r\n"),
+        "forms.uai": "BAYES\n" + body.replace("0.25 0.75", ".25 7.5e-1").replace("1 2 3", "1. 2E0 -0"),
+        "plus.uai": "BAYES\n" + body.replace("0.25", "+0.25"),
+        "subnormal.uai": "BAYES\n" + body.replace("0.25", "1e-320"),
+        "huge.uai": "BAYES\n" + body.replace("0.25", "1e400"),
+        "hexfloat.uai": "BAYES\n" + body.replace("0.25", "0x1p-2"),
+        "junk_int.uai": "BAYES\n" + body.replace("2 3", "2 3abc", 1),
+        "truncated.uai": "BAYES\n" + body[:-8],
+        "bad_scope.uai": "BAYES\n" + body.replace("2 0 1", "2 0 7"),
+        "header.uai": "BAYESIAN\n" + body,
+        "empty.uai": "",
+    }
+    paths = []
+    for name, text in odd.items():
+        f = tmp_path / name
+        f.write_bytes(text.encode())
+        paths.append(f)
+    rc, rows = _check(paths)
+    assert rc == 0, rows
+    assert rows["comments.uai"] == "SAME" and rows["crlf.uai"] == "SAME" and rows["forms.uai"] == "SAME", rows
+    for name in ("plus.uai", "subnormal.uai", "huge.uai", "hexfloat.uai", "junk_int.uai", "truncated.uai", "bad_scope.uai",
+                 "header.uai", "empty.uai"):
+        assert rows[name] == "FALLBACK", (name, rows[name])
