@@ -185,7 +185,38 @@ def union_entries(scopes, order):
     return total
 
 
-def config5_leg(ctx, steps, warmup):
+def config5_cpu_leg(text, evs, procs=None, per_proc=2):
+    """the reference's BN::partition (-mf) on the first evidence sets of config 5: `procs` harness processes side by
+    side (the reference is single-threaded), `per_proc` queries each -> (queries/s, cores, kind, Z of set 0)"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import concurrent.futures
+    import oracle as orc
+    if not orc.have_ref():
+        return None
+    if procs is None:
+        procs = max(1, min(os.cpu_count() or 1, 32))
+    path = "/tmp/bnpp_cpu_config5_%d.uai" % os.getpid()
+    with open(path, "w") as f:
+        f.write(text)
+
+    def one(i):
+        script = ["model " + path]
+        for ev in evs[i * per_proc:(i + 1) * per_proc]:
+            script += ["evidset %d %s" % (len(ev), " ".join("%d %d" % kv for kv in sorted(ev.items()))), "opt mf", "pr"]
+        rows = orc.RefHarness().run(script, timeout=600)
+        return [float(r[1]) for r in rows if r[0] == "PR"]
+    t0 = time.perf_counter()
+    with concurrent.futures.ThreadPoolExecutor(procs) as ex:
+        res = list(ex.map(one, range(procs)))
+    wall = time.perf_counter() - t0
+    os.unlink(path)
+    n = sum(len(r) for r in res)
+    return {"value": n / wall, "unit": "queries/s", "cores": procs, "kind": "reference",
+            "sample": "%d evidence sets of the same batch, %d concurrent single-threaded reference processes x %d queries "
+                      "(model load included), %.2f s wall" % (n, procs, per_proc, wall)}, res[0][0]
+
+
+def config5_leg(ctx, steps, warmup, cpu_arm=True):
     """The other half of BASELINE.json's metric -- VE PR queries/sec -- on config 5: 65 536 evidence sets on
     the 500-variable BN, PR per set, one GPU (tools/batch_bench.py is the multi-GPU version).  Device-timed
     with the evidence resident, and end to end from pinned host evidence (ordering, planning, H2D, the
@@ -193,7 +224,8 @@ def config5_leg(ctx, steps, warmup):
     import torch
     from bnpp_b200 import model, synth
     N, W, K, seed, nobs, nsets = 500, 6, 3, 11, 20, 65536
-    _, bn = model.from_uai_text(ctx, synth.random_bn_uai(N, W, K, seed))
+    text = synth.random_bn_uai(N, W, K, seed)
+    _, bn = model.from_uai_text(ctx, text)
     evs = synth.evidence_batch(N, nobs, nsets, seed=5, fixed_ids=True)
     observed = sorted(evs[0])
     host = torch.tensor([[ev[v] for v in observed] for ev in evs], dtype=torch.uint8).pin_memory()
@@ -225,6 +257,14 @@ def config5_leg(ctx, steps, warmup):
         per_iter.append((time.perf_counter() - t0) * 1e3)
     e2e_ms = sum(per_iter) / len(per_iter)
     bn.close()
+    cpu = None
+    try:
+        got = config5_cpu_leg(text, evs) if cpu_arm else None
+        if got:
+            cpu, z_ref = got
+            cpu["Z_set0_reference"], cpu["Z_set0_gpu"] = z_ref, float(zh[0])
+    except Exception as e:
+        cpu = {"error": "%s: %s" % (type(e).__name__, e)}
     return {"metric": "VE PR queries/sec", "value": nsets / ms * 1e3, "unit": "queries/s", "ms_per_batch": ms,
             "config": {"workload": "config 5: %d evidence sets, synthetic BN N=%d W=%d K=%d seed=%d, %d observed ids fixed, "
                                    "PR per set via VE (min-fill)" % (nsets, N, W, K, seed, nobs)},
@@ -233,7 +273,7 @@ def config5_leg(ctx, steps, warmup):
             "gpu_launches_per_batch": launches, "union_entries_per_s": union_entries * nsets / ms * 1e3,
             "kernel": ("ve_fused: one launch, %d lanes per evidence set, %d doubles of shared memory per set, %d steps"
                        % (lanes, arena, n_steps)) if lanes else "contract_batched: one launch per bucket",
-            "sample_Z": zh[:2].tolist()}
+            "sample_Z": zh[:2].tolist(), "cpu_baseline": cpu}
 
 
 def main():
@@ -417,7 +457,7 @@ def main():
     config5 = None
     if n_gpus == 1 and not args.no_config5:
         try:
-            config5 = config5_leg(ctx, args.steps, args.warmup)
+            config5 = config5_leg(ctx, args.steps, args.warmup, cpu_arm=not args.no_cpu_baseline)
         except Exception as e:      # the headline line must not depend on the auxiliary leg
             config5 = {"error": "%s: %s" % (type(e).__name__, e)}
 
