@@ -150,3 +150,29 @@ def test_fused_program_random_mixed_cardinalities():
             p.close()
             checked += 1
     assert checked >= 120
+
+
+def test_plan_with_large_variable_ids():
+    """variable ids are arbitrary uint32 at the ABI: ids far beyond the dense rank table plan, order and
+    evaluate like the same network with small ids"""
+    import oracle as orc
+    cards_small = [2, 3, 2, 2]
+    scopes_small = [[0], [1, 0], [2, 1], [3, 2, 0]]
+    rng = np.random.default_rng(7)
+    tables = [rng.uniform(0.1, 1.0, int(np.prod([cards_small[v] for v in sc]))) for sc in scopes_small]
+    want = orc.partition(orc.OModel("MARKOV", cards_small, [orc.OFactor(sc, t) for sc, t in zip(scopes_small, tables)]), {2: 1},
+                         [0, 1, 3])
+    base = (1 << 23) + 5                                  # beyond RankMap's dense range (ve.cu)
+    ids = {v: base + 1000 * v for v in range(4)}
+    scopes = [[ids[v] for v in sc] for sc in scopes_small]
+
+    class Cards(dict):                                    # model._scopes indexes cards by variable id
+        pass
+    cards = Cards({ids[v]: cards_small[v] for v in range(4)})
+    p = DryPlan(cards, scopes, [ids[2]], [ids[0], ids[1], ids[3]])
+    G, arena, n_steps = p.fused_info(1)
+    assert G > 0
+    prog, tab = p.program(1)
+    res, _ = interpret(prog, tab, n_steps, arena, tables, [1], 1)
+    assert math.isclose(res[0], want, rel_tol=1e-12)
+    p.close()
