@@ -176,3 +176,42 @@ def test_plan_with_large_variable_ids():
     res, _ = interpret(prog, tab, n_steps, arena, tables, [1], 1)
     assert math.isclose(res[0], want, rel_tol=1e-12)
     p.close()
+
+
+def test_fused_marginals_random_networks():
+    """the all-marginals (bucket-tree) plan as a fused program on random mixed-cardinality networks with evidence,
+    against the brute-force joint marginals of the oracle (code/model.cpp:69-101)"""
+    import random
+    import oracle as orc
+    rng = random.Random(77)
+    checked = 0
+    for trial in range(25):
+        n = rng.randint(3, 8)
+        cards = [rng.randint(2, 4) for _ in range(n)]
+        scopes, tables = [[v] for v in range(n)], []          # every variable is mentioned by a unary factor
+        for _ in range(rng.randint(n - 1, 2 * n)):
+            scopes.append(rng.sample(range(n), rng.randint(2, min(3, n))))
+        for sc in scopes:
+            tables.append(np.array([rng.uniform(0.05, 2.0) for _ in range(int(np.prod([cards[v] for v in sc])))]))
+        ev = {v: rng.randrange(cards[v]) for v in rng.sample(range(n), rng.randint(0, 2))}
+        m = orc.OModel("MARKOV", cards, [orc.OFactor(sc, t) for sc, t in zip(scopes, tables)])
+        want = orc.joint_marginals(m, ev)
+        observed = sorted(ev)
+        variables = [v for v in range(n) if v not in ev]
+        for flag in ("mf", "md"):
+            order = _order(cards, scopes, variables, ev, flag)
+            p = DryPlan(cards, scopes, observed, order, marginals=True)
+            G, arena, n_steps = p.fused_info(1)
+            assert G > 0
+            off, size, total = p.layout
+            prog, tab = p.program(1)
+            res, _ = interpret(prog, tab, n_steps, arena, tables, [ev[v] for v in observed], total)
+            for v in range(n):
+                if v in ev:
+                    assert size[v] == 1
+                    continue
+                seg = res[off[v]:off[v] + size[v]]
+                assert np.allclose(seg / seg.sum(), want[v].values, rtol=1e-10, atol=0.0), (trial, flag, v)
+            p.close()
+            checked += 1
+    assert checked == 50
