@@ -685,6 +685,9 @@ int fused_pick(bnpp_ve_plan *pl, uint32_t nb)
     while (fp.total_union / G > kFusedMaxLaneWork && G < 128) G = G < 32 ? 2 * G : 128;
     if (fp.total_union / G > kFusedMaxLaneWork) return 0;
     if (fused_smem_bytes(G, fp.arena) > kFusedSmemLimit) return 0;
+    // a batch wants many resident CTAs (the kernel hides latency with warps, measured: 4 -> 7 CTAs per SM = 5.6 -> 3.5 ms);
+    // an arena that allows fewer than four per SM is better served by one launch per bucket
+    if (nb > 1 && fused_smem_bytes(G, fp.arena) > (56u << 10)) return 0;
     return G;
 }
 

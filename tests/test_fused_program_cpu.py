@@ -144,9 +144,10 @@ def test_fused_program_random_mixed_cardinalities():
             prog, tab = p.program(1)
             res, z = interpret(prog, tab, n_steps, arena, tables, [ev[v] for v in observed], 1)
             assert math.isclose(res[0], want, rel_tol=1e-12), (trial, flag, res[0], want)
-            # a batch program of the same plan is the same program
-            prog_b, tab_b = p.program(512)
-            assert np.array_equal(prog, prog_b) and np.array_equal(tab, tab_b)
+            # a batch of the same plan runs the same program (when its arena leaves room for enough CTAs per SM)
+            if p.fused_info(512)[0]:
+                prog_b, tab_b = p.program(512)
+                assert np.array_equal(prog, prog_b) and np.array_equal(tab, tab_b)
             p.close()
             checked += 1
     assert checked >= 120
