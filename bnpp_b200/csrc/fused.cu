@@ -207,6 +207,9 @@ __global__ void __launch_bounds__(kFusedThreads) ve_fused(const __grid_constant_
             if (flags & kFusedToResult) {
                 d.result = p.result + ((uint64_t)h0.w * p.nb + b);
                 d.stride = p.nb;
+            } else if (flags & kFusedToGlobal) {      // single queries inside a launch-per-bucket plan: a later launch reads it
+                d.result = reinterpret_cast<double *>(((uint64_t)h1.z << 32) | (uint64_t)h1.y);
+                d.stride = 1;
             } else {
                 d.result = nullptr;
                 d.stride = 0;

@@ -24,7 +24,8 @@ constexpr int kFusedInlineEv = 256;     // single query: evidence values travel 
 //   [2] k | flags << 8
 //   [3] out_off   arena offset of the output, or offset into the result buffer (kFusedToResult)
 //   [4] tab_off   first word of this step's operand-offset table [k][n_out] in `offtab`
-//   [5..7] reserved
+//   [5..6] device address of the output (kFusedToGlobal: a later launch of the plan reads it)
+//   [7] reserved
 // then k operand records, 4 words each
 //   [0] kind | nobs << 8     kind 0: intermediate in the arena, 1: resident CPT view
 //   [1] arena offset         | low  32 bits of the CPT's device address
@@ -33,6 +34,7 @@ constexpr int kFusedInlineEv = 256;     // single query: evidence values travel 
 // each CPT operand followed by its observed axes, (stride, evidence column) pairs padded to 4 words
 constexpr uint32_t kFusedToResult = 1u;     // flags
 constexpr uint32_t kFusedWantZ = 2u;
+constexpr uint32_t kFusedToGlobal = 8u;     // the output goes to the device address in header words 5 (low) and 6 (high), dense
 constexpr uint32_t kFusedPairs = 4u;        // cx == 2 and every arena operand holds the eliminated variable at stride 1 on even offsets
 constexpr uint32_t kFusedHeaderWords = 8;
 constexpr uint32_t kFusedOperandWords = 4;

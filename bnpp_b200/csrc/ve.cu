@@ -83,8 +83,11 @@ private:
 struct FusedProgram {
     bool built = false, ok = false;
     std::vector<uint32_t> prog, offtab;
-    std::vector<std::pair<uint32_t, int>> ptr_slots;    // (first word of a CPT operand record, input table it views)
-    std::vector<const double *> tables;                 // the table addresses `prog` holds right now
+    // 64-bit device addresses inside `prog`, written at run time: (word of the low half, word of the high half,
+    // what it points to: input table `index` (kind 0) or the plan-arena slot of intermediate `index` (kind 1))
+    struct Slot { uint32_t lo, hi; int kind, index; };
+    std::vector<Slot> ptr_slots;
+    std::vector<uint64_t> slot_addr;                    // the addresses `prog` holds right now
     uint32_t n_steps = 0, arena = 0, max_out = 0;
     uint64_t total_union = 0;                           // union entries of all steps, per evidence set
     uint32_t *prog_dev = nullptr, *offtab_dev = nullptr;
@@ -98,6 +101,14 @@ struct bnpp_ve_plan {
     int n_obs = 0;
     int fused_mode = 1;                     // 0: one launch per bucket always; 1: one launch per plan when every step is small
     bnpp::FusedProgram fused;
+    // EXPERIMENTAL (off unless BNPP_FUSED_SEGMENTS=1 or bnpp_ve_plan_set_segments): inside a launch-per-bucket plan,
+    // every run of consecutive small steps is one ve_fused launch (DESIGN.md gap 4)
+    struct Segment { int a = 0, b = 0, G = 0; bnpp::FusedProgram prog; };
+    int segments_mode = 0;
+    uint32_t segments_max_steps = 0;        // > 0: cut runs into pieces of at most this many steps (tests)
+    bool segments_built = false;
+    std::vector<Segment> segs;
+    std::vector<int> seg_at;                // per step: the segment that STARTS here, or -1
     std::vector<bnpp::PlanFactor> f;
     std::vector<bnpp::PlanStep> steps;
     std::vector<uint32_t> result_var, result_card;
@@ -437,6 +448,8 @@ bool fused_default_on()
 // at any time -- the arena of one evidence set has to fit in shared memory many times over.
 // Any topological order gives the same numbers: operand lists, hence the order of the
 // multiplications inside a bucket, are untouched.
+void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment, FusedProgram &fp);
+
 void fused_build(bnpp_ve_plan *pl)
 {
     FusedProgram &fp = pl->fused;
@@ -497,13 +510,42 @@ void fused_build(bnpp_ve_plan *pl)
         done[root] = 1;
     }
     if (order.size() != ns) return;
+    fused_encode(pl, order, false, fp);
+}
 
-    // arena of one evidence set: first fit over the new order, in doubles
-    std::vector<int> pos(ns, 0), last_use(pl->f.size(), -1);
+// The program of the steps `order` (plan step indices, a topological order).  segment = false: the whole plan.
+// segment = true: a run of steps inside a launch-per-bucket plan -- intermediates made by earlier launches are read
+// from the plan's global arena (operand kind 1 without observed axes), an output that a LATER launch reads is
+// written there (kFusedToGlobal); only intermediates born and consumed inside the run live in shared memory.
+void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment, FusedProgram &fp)
+{
+    fp.built = true;
+    fp.ok = false;
+    const size_t ns = order.size(), all = pl->steps.size();
+    if (ns == 0) return;
+    std::vector<int> pos(all, -1), last_use(pl->f.size(), -1), producer(pl->f.size(), -1);
     for (size_t i = 0; i < ns; ++i) pos[order[i]] = (int)i;
-    for (size_t s = 0; s < ns; ++s)
-        for (int id : pl->steps[s].operands)
-            if (pl->f[id].src < 0) last_use[id] = std::max(last_use[id], pos[s]);
+    for (size_t s = 0; s < all; ++s)
+        if (pl->steps[s].out >= 0) producer[pl->steps[s].out] = (int)s;
+    // an intermediate lives in shared memory iff it is made here; then every reader must be here too
+    std::vector<char> in_smem(pl->f.size(), 0), read_inside(pl->f.size(), 0), read_outside(pl->f.size(), 0);
+    for (size_t s = 0; s < all; ++s)
+        for (int id : pl->steps[s].operands) {
+            if (pl->f[id].src >= 0) continue;
+            if (pos[s] >= 0) {
+                read_inside[id] = 1;
+                last_use[id] = std::max(last_use[id], pos[s]);
+            } else {
+                read_outside[id] = 1;
+            }
+        }
+    for (size_t i = 0; i < pl->f.size(); ++i) {
+        if (pl->f[i].src >= 0 || producer[i] < 0 || pos[producer[i]] < 0) continue;
+        if (!segment) in_smem[i] = 1;
+        else if (read_inside[i] && read_outside[i]) return;       // two homes: not a run this builder takes
+        else in_smem[i] = read_inside[i];
+    }
+    // arena of one evidence set: first fit over the order, in doubles
     std::vector<uint64_t> aoff(pl->f.size(), 0);
     std::vector<std::pair<uint64_t, uint64_t>> free_list;   // (offset, size)
     uint64_t top = 0, peak = 0;
@@ -537,17 +579,18 @@ void fused_build(bnpp_ve_plan *pl)
     };
     for (size_t i = 0; i < ns; ++i) {
         const PlanStep &st = pl->steps[order[i]];
-        if (st.out >= 0) {
+        if (st.out >= 0 && in_smem[st.out]) {
             aoff[st.out] = take(pl->f[st.out].size);
             peak = std::max(peak, top);
         }
         std::vector<int> seen;
         for (int id : st.operands) {
-            if (pl->f[id].src >= 0 || last_use[id] != (int)i || std::find(seen.begin(), seen.end(), id) != seen.end()) continue;
+            if (pl->f[id].src >= 0 || !in_smem[id] || last_use[id] != (int)i || std::find(seen.begin(), seen.end(), id) != seen.end())
+                continue;
             seen.push_back(id);
             give(aoff[id], pl->f[id].size);
         }
-        if (st.out >= 0 && last_use[st.out] < 0) give(aoff[st.out], pl->f[st.out].size);   // never read
+        if (st.out >= 0 && in_smem[st.out] && last_use[st.out] < 0) give(aoff[st.out], pl->f[st.out].size);   // never read
     }
     if (peak >= (1ull << 24)) return;
 
@@ -613,7 +656,7 @@ void fused_build(bnpp_ve_plan *pl)
         // the pair form: binary eliminated variable at stride 1 in every arena operand, on even offsets
         bool pairs = cx == 2;
         for (int q = 0; q < k && pairs; ++q) {
-            if (pl->f[st.operands[q]].src >= 0) continue;
+            if (pl->f[st.operands[q]].src >= 0 || !in_smem[st.operands[q]]) continue;
             pairs = sx[q] == 1;
             for (uint64_t o = 0; o < n_out && pairs; ++o) pairs = (fp.offtab[tab_off + (size_t)q * n_out + o] & 1u) == 0;
         }
@@ -622,22 +665,37 @@ void fused_build(bnpp_ve_plan *pl)
             flags |= kFusedToResult | (st.want_z ? kFusedWantZ : 0u);
             if (st.roff >= (1ull << 32)) return;
             out_off = (uint32_t)st.roff;
-        } else {
+        } else if (in_smem[st.out]) {
             out_off = (uint32_t)aoff[st.out];
+        } else {
+            flags |= kFusedToGlobal;      // a later launch reads it: absolute address in header words 5-6
+            out_off = 0;
         }
         const uint32_t head[kFusedHeaderWords] = {(uint32_t)n_out, cx, (uint32_t)k | (flags << 8), out_off, tab_off, 0, 0, 0};
+        if (flags & kFusedToGlobal) {
+            const uint32_t at = (uint32_t)fp.prog.size();
+            fp.ptr_slots.push_back({at + 5, at + 6, 1, st.out});
+        }
         fp.prog.insert(fp.prog.end(), head, head + kFusedHeaderWords);
         for (int q = 0; q < k; ++q) {
             const PlanFactor &pf = pl->f[st.operands[q]];
             const uint32_t at = (uint32_t)fp.prog.size();
-            if (pf.src < 0) {
+            if (pf.src < 0 && in_smem[st.operands[q]]) {
                 const uint32_t rec[kFusedOperandWords] = {0u, (uint32_t)aoff[st.operands[q]], (uint32_t)sx[q], 0u};
                 fp.prog.insert(fp.prog.end(), rec, rec + kFusedOperandWords);
                 continue;
             }
+            if (pf.src < 0) {
+                // made by an earlier launch: a global table like a CPT, without observed axes
+                if (producer[st.operands[q]] < 0 || pos[producer[st.operands[q]]] >= 0) return;
+                const uint32_t rec[kFusedOperandWords] = {1u, 0u, (uint32_t)sx[q], 0u};
+                fp.prog.insert(fp.prog.end(), rec, rec + kFusedOperandWords);
+                fp.ptr_slots.push_back({at + 1, at + 3, 1, st.operands[q]});
+                continue;
+            }
             const uint32_t rec[kFusedOperandWords] = {1u | ((uint32_t)pf.obs.size() << 8), 0u, (uint32_t)sx[q], 0u};
             fp.prog.insert(fp.prog.end(), rec, rec + kFusedOperandWords);
-            fp.ptr_slots.push_back({at, pf.src});
+            fp.ptr_slots.push_back({at + 1, at + 3, 0, pf.src});
             for (size_t j = 0; j < pf.obs.size(); j += 2) {
                 uint32_t pair[4] = {(uint32_t)pf.obs[j].first, (uint32_t)pf.obs[j].second, 0u, 0u};
                 if (pf.obs[j].first >= (1ll << 32)) return;
@@ -653,9 +711,9 @@ void fused_build(bnpp_ve_plan *pl)
     if (fp.prog.size() >= (1ull << 31)) return;
     fp.n_steps = (uint32_t)ns;
     fp.total_union = 0;
-    for (const PlanStep &st : pl->steps) fp.total_union += st.union_entries;
+    for (int s : order) fp.total_union += pl->steps[s].union_entries;
     fp.arena = (uint32_t)std::max<uint64_t>((peak + 1) & ~1ull, 2);
-    fp.tables.assign(pl->n_inputs, nullptr);
+    fp.slot_addr.assign(fp.ptr_slots.size(), 0);
     fp.ok = true;
 }
 
@@ -691,19 +749,79 @@ int fused_pick(bnpp_ve_plan *pl, uint32_t nb)
     return G;
 }
 
+bool segments_default_on()
+{
+    static const int on = [] {
+        const char *e = getenv("BNPP_FUSED_SEGMENTS");
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    return on != 0;
+}
+
+// runs of consecutive small steps, in plan order (single queries only)
+void build_segments(bnpp_ve_plan *pl)
+{
+    pl->segments_built = true;
+    pl->segs.clear();
+    const size_t ns = pl->steps.size();
+    pl->seg_at.assign(ns, -1);
+    auto small = [&](size_t s) {
+        const PlanStep &st = pl->steps[s];
+        return st.union_entries <= kFusedMaxUnion && !st.operands.empty() && (int)st.operands.size() <= kMaxK;
+    };
+    const size_t min_len = pl->segments_max_steps ? 1 : 2;
+    size_t s = 0;
+    while (s < ns) {
+        if (!small(s)) { ++s; continue; }
+        size_t e = s;
+        while (e < ns && small(e) && (!pl->segments_max_steps || e - s < pl->segments_max_steps)) ++e;
+        if (e - s >= min_len) {
+            bnpp_ve_plan::Segment seg;
+            seg.a = (int)s;
+            seg.b = (int)e;
+            std::vector<int> order;
+            for (size_t i = s; i < e; ++i) order.push_back((int)i);
+            fused_encode(pl, order, true, seg.prog);
+            if (seg.prog.ok) {
+                int G = seg.prog.max_out >= 128 ? 128 : 32;
+                if (fused_smem_bytes(G, seg.prog.arena) > kFusedSmemLimit) G = 128;
+                if (seg.prog.total_union / G > kFusedMaxLaneWork && G < 128) G = 128;
+                if (seg.prog.total_union / G <= kFusedMaxLaneWork && fused_smem_bytes(G, seg.prog.arena) <= kFusedSmemLimit) {
+                    seg.G = G;
+                    pl->seg_at[s] = (int)pl->segs.size();
+                    pl->segs.push_back(std::move(seg));
+                }
+            }
+        }
+        s = e;
+    }
+}
+
+int run_fused(bnpp_ve_plan *pl, FusedProgram &fp, int G, const double *const *tables_dev, uint32_t nb, const uint8_t *ev_dev,
+              const uint32_t *obs_val, double *result_dev, double *z_dev);
+
 int run_fused(bnpp_ve_plan *pl, int G, const double *const *tables_dev, uint32_t nb, const uint8_t *ev_dev,
               const uint32_t *obs_val, double *result_dev, double *z_dev)
 {
+    return run_fused(pl, pl->fused, G, tables_dev, nb, ev_dev, obs_val, result_dev, z_dev);
+}
+
+int run_fused(bnpp_ve_plan *pl, FusedProgram &fp, int G, const double *const *tables_dev, uint32_t nb, const uint8_t *ev_dev,
+              const uint32_t *obs_val, double *result_dev, double *z_dev)
+{
     bnpp_ctx *ctx = pl->ctx;
-    FusedProgram &fp = pl->fused;
+    auto address = [&](const FusedProgram::Slot &slot) {
+        return slot.kind == 0 ? reinterpret_cast<uint64_t>(tables_dev[slot.index])
+                              : reinterpret_cast<uint64_t>(pl->arena + pl->arena_off[slot.index]);
+    };
     bool moved = fp.prog_dev == nullptr;
-    for (auto &slot : fp.ptr_slots) moved = moved || fp.tables[slot.second] != tables_dev[slot.second];
+    for (size_t i = 0; i < fp.ptr_slots.size(); ++i) moved = moved || fp.slot_addr[i] != address(fp.ptr_slots[i]);
     if (moved) {
-        for (auto &slot : fp.ptr_slots) {
-            const uint64_t a = reinterpret_cast<uint64_t>(tables_dev[slot.second]);
-            fp.prog[slot.first + 1] = (uint32_t)a;
-            fp.prog[slot.first + 3] = (uint32_t)(a >> 32);
-            fp.tables[slot.second] = tables_dev[slot.second];
+        for (size_t i = 0; i < fp.ptr_slots.size(); ++i) {
+            const uint64_t a = address(fp.ptr_slots[i]);
+            fp.prog[fp.ptr_slots[i].lo] = (uint32_t)a;
+            fp.prog[fp.ptr_slots[i].hi] = (uint32_t)(a >> 32);
+            fp.slot_addr[i] = a;
         }
         if (!fp.prog_dev) {
             double *store = nullptr;
@@ -753,6 +871,7 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
     pl->n_inputs = nfac;
     pl->n_obs = n_obs;
     pl->fused_mode = fused_default_on() ? 1 : 0;
+    pl->segments_mode = segments_default_on() ? 1 : 0;
 
     std::map<uint32_t, int> obs_index;
     for (int i = 0; i < n_obs; ++i) obs_index[obs_var[i]] = i;
@@ -834,6 +953,7 @@ int bnpp_mar_plan_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfa
     pl->n_inputs = nfac;
     pl->n_obs = n_obs;
     pl->fused_mode = fused_default_on() ? 1 : 0;
+    pl->segments_mode = segments_default_on() ? 1 : 0;
     pl->is_mar = true;
     std::map<uint32_t, int> obs_index;
     for (int i = 0; i < n_obs; ++i) obs_index[obs_var[i]] = i;
@@ -971,6 +1091,10 @@ int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
     if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
     if (pl->graph) cudaGraphDestroy(pl->graph);
     if (pl->arena) bnpp_free(pl->ctx, pl->arena);
+    for (auto &seg : pl->segs) {
+        if (seg.prog.prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(seg.prog.prog_dev));
+        if (seg.prog.offtab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(seg.prog.offtab_dev));
+    }
     if (pl->fused.prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.prog_dev));
     if (pl->fused.offtab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.offtab_dev));
     if (pl->mar_off_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->mar_off_dev));
@@ -1030,6 +1154,65 @@ int bnpp_ve_plan_fused_info(bnpp_ve_plan *pl, uint32_t nb, int32_t *lanes_per_se
     return BNPP_OK;
 }
 
+int bnpp_ve_plan_set_segments(bnpp_ve_plan *pl, int on, uint32_t max_steps)
+{
+    if (!pl) return BNPP_EINVAL;
+    pl->segments_mode = on != 0;
+    pl->segments_max_steps = max_steps;
+    pl->segments_built = false;
+    for (auto &seg : pl->segs) {
+        if (seg.prog.prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(seg.prog.prog_dev));
+        if (seg.prog.offtab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(seg.prog.offtab_dev));
+    }
+    pl->segs.clear();
+    return BNPP_OK;
+}
+
+static int dump_program(const FusedProgram &fp, uint32_t *prog, uint64_t prog_cap, uint64_t *prog_words, uint32_t *offtab,
+                        uint64_t tab_cap, uint64_t *tab_words)
+{
+    if (prog_words) *prog_words = fp.prog.size();
+    if (tab_words) *tab_words = fp.offtab.size();
+    if (prog) {
+        if (prog_cap < fp.prog.size()) return BNPP_EINVAL;
+        std::copy(fp.prog.begin(), fp.prog.end(), prog);
+        for (auto &slot : fp.ptr_slots) {
+            prog[slot.lo] = (uint32_t)slot.index;
+            prog[slot.hi] = slot.kind == 0 ? 0xffffffffu : 0xfffffffeu;      // input table | plan-arena intermediate
+        }
+    }
+    if (offtab) {
+        if (tab_cap < fp.offtab.size()) return BNPP_EINVAL;
+        std::copy(fp.offtab.begin(), fp.offtab.end(), offtab);
+    }
+    return BNPP_OK;
+}
+
+// segments of a launch-per-bucket plan (experimental): [a, b) step ranges, lanes, arena, and each one's program
+int bnpp_ve_plan_segments(bnpp_ve_plan *pl, uint32_t cap, uint32_t *n, uint32_t *first_step, uint32_t *end_step,
+                          int32_t *lanes, uint32_t *arena_doubles)
+{
+    if (!pl || !n) return BNPP_EINVAL;
+    if (!pl->segments_built) build_segments(pl);
+    *n = (uint32_t)pl->segs.size();
+    for (uint32_t i = 0; i < *n && i < cap; ++i) {
+        if (first_step) first_step[i] = (uint32_t)pl->segs[i].a;
+        if (end_step) end_step[i] = (uint32_t)pl->segs[i].b;
+        if (lanes) lanes[i] = pl->segs[i].G;
+        if (arena_doubles) arena_doubles[i] = pl->segs[i].prog.arena;
+    }
+    return BNPP_OK;
+}
+
+int bnpp_ve_plan_segment_program(bnpp_ve_plan *pl, uint32_t segment, uint32_t *prog, uint64_t prog_cap, uint64_t *prog_words,
+                                 uint32_t *offtab, uint64_t tab_cap, uint64_t *tab_words)
+{
+    if (!pl) return BNPP_EINVAL;
+    if (!pl->segments_built) build_segments(pl);
+    if (segment >= pl->segs.size()) return BNPP_EINVAL;
+    return dump_program(pl->segs[segment].prog, prog, prog_cap, prog_words, offtab, tab_cap, tab_words);
+}
+
 // The step program a fused run over nb sets would execute (fused.hpp), for inspection and for the
 // CPU interpreter of the tests: CPT operand records carry the INDEX of their input table in word 1
 // and 0xffffffff in word 3 instead of a device address.
@@ -1044,20 +1227,7 @@ int bnpp_ve_plan_fused_program(bnpp_ve_plan *pl, uint32_t nb, uint32_t *prog, ui
     if (prog_words) *prog_words = G ? pl->fused.prog.size() : 0;
     if (tab_words) *tab_words = G ? pl->fused.offtab.size() : 0;
     if (!G) return BNPP_OK;
-    const FusedProgram &fp = pl->fused;
-    if (prog) {
-        if (prog_cap < fp.prog.size()) return BNPP_EINVAL;
-        std::copy(fp.prog.begin(), fp.prog.end(), prog);
-        for (auto &slot : fp.ptr_slots) {
-            prog[slot.first + 1] = (uint32_t)slot.second;
-            prog[slot.first + 3] = 0xffffffffu;
-        }
-    }
-    if (offtab) {
-        if (tab_cap < fp.offtab.size()) return BNPP_EINVAL;
-        std::copy(fp.offtab.begin(), fp.offtab.end(), offtab);
-    }
-    return BNPP_OK;
+    return dump_program(pl->fused, prog, prog_cap, prog_words, offtab, tab_cap, tab_words);
 }
 
 int bnpp_ve_plan_step_stats(bnpp_ve_plan *pl, uint64_t n, float *ms, uint64_t *bytes, uint64_t *entries, int32_t *k)
@@ -1161,11 +1331,9 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
     }
     int rc = BNPP_OK;
     int fused_g = 0;
-    if (pl->n_obs <= kFusedInlineEv) {
-        bool bytes = true;
-        for (int i = 0; i < pl->n_obs; ++i) bytes = bytes && obs_val[i] <= 255;
-        if (bytes) fused_g = fused_pick(pl, 1);
-    }
+    bool ev_inline = pl->n_obs <= kFusedInlineEv;      // the evidence values travel in the kernel parameters as bytes
+    for (int i = 0; i < pl->n_obs && ev_inline; ++i) ev_inline = obs_val[i] <= 255;
+    if (ev_inline) fused_g = fused_pick(pl, 1);
     if (fused_g) {
         // K9: every step is small -- the whole plan is one launch, intermediates in shared memory
         rc = run_fused(pl, fused_g, tables_dev, 1, nullptr, obs_val, result_dev, z_dev);
@@ -1182,7 +1350,10 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
         }
         for (size_t i = 0; i < pl->f.size(); ++i)
             if (pl->f[i].src < 0) ptr[i] = pl->arena + pl->arena_off[i];
-        const bool graphed = pl->use_graph && !pl->profiling && pl->steps.size() > 1 && pl->runs >= 1;
+        // experimental: runs of consecutive small steps as one ve_fused launch each (plain launches, no graph)
+        const bool seg_on = pl->segments_mode && ev_inline && !pl->profiling;
+        if (seg_on && !pl->segments_built) build_segments(pl);
+        const bool graphed = pl->use_graph && !pl->profiling && pl->steps.size() > 1 && pl->runs >= 1 && !seg_on;
         bool fresh = false;
         if (graphed && !pl->graph_exec) {
             if (cudaGraphCreate(&pl->graph, 0) != cudaSuccess) pl->use_graph = false;
@@ -1190,6 +1361,12 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             fresh = true;
         }
         for (size_t s = 0; s < pl->steps.size() && rc == BNPP_OK; ++s) {
+            if (seg_on && pl->seg_at[s] >= 0) {
+                bnpp_ve_plan::Segment &sg = pl->segs[pl->seg_at[s]];
+                rc = run_fused(pl, sg.prog, sg.G, tables_dev, 1, nullptr, obs_val, result_dev, z_dev);
+                s = (size_t)sg.b - 1;
+                continue;
+            }
             const PlanStep &st = pl->steps[s];
             if (pl->profiling) cudaEventRecord(pl->ev[s], ctx->stream);
             const double *in[kMaxK];

@@ -38,6 +38,7 @@ def _declare(L):
     L.bnpp_ve_plan_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.bnpp_ve_plan_set_fused.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.bnpp_ve_plan_fused_info.argtypes = [ctypes.c_void_p, ctypes.c_uint32, P(ctypes.c_int32), capi.c_u32p, capi.c_u32p]
+    L.bnpp_ve_plan_set_segments.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32]
     L.bnpp_ve_plan_step_stats.argtypes = [ctypes.c_void_p, ctypes.c_uint64, P(ctypes.c_float), capi.c_u64p, capi.c_u64p,
                                           P(ctypes.c_int32)]
     L.bnpp_ve_plan_step_kernel.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_size_t]
@@ -136,6 +137,10 @@ class VEPlan:
     def set_fused(self, on=True):
         """one launch for the whole plan when every step is small (default), or one launch per bucket"""
         self.ctx.check(self.ctx.L.bnpp_ve_plan_set_fused(self.h, int(on)))
+
+    def set_segments(self, on=True, max_steps=0):
+        """EXPERIMENTAL: inside a launch-per-bucket plan, every run of consecutive small steps as one ve_fused launch"""
+        self.ctx.check(self.ctx.L.bnpp_ve_plan_set_segments(self.h, int(on), int(max_steps)))
 
     def fused_info(self, nb=1):
         """-> (lanes per evidence set, 0 = a run over nb sets is not fused; shared-memory doubles per set; steps)"""

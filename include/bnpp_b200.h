@@ -208,6 +208,16 @@ int bnpp_ve_plan_fused_info(bnpp_ve_plan *plan, uint32_t nb, int32_t *lanes_per_
  * Pass NULL buffers to query the sizes.  Works on dry plans (created with ctx == NULL). */
 int bnpp_ve_plan_fused_program(bnpp_ve_plan *plan, uint32_t nb, uint32_t *prog, uint64_t prog_cap, uint64_t *prog_words,
                                uint32_t *offtab, uint64_t tab_cap, uint64_t *tab_words);
+/* EXPERIMENTAL, off by default (environment BNPP_FUSED_SEGMENTS=1 turns it on for new plans): inside a plan that
+ * runs one launch per bucket, every run of consecutive small steps becomes ONE ve_fused launch (single queries);
+ * max_steps > 0 cuts the runs into pieces of at most that many steps (tests).  _segments lists the step ranges,
+ * _segment_program dumps one segment's program like _fused_program (0xfffffffe in an address's high word: the
+ * intermediate with that index in the plan's global arena). */
+int bnpp_ve_plan_set_segments(bnpp_ve_plan *plan, int on, uint32_t max_steps);
+int bnpp_ve_plan_segments(bnpp_ve_plan *plan, uint32_t cap, uint32_t *n, uint32_t *first_step, uint32_t *end_step,
+                          int32_t *lanes, uint32_t *arena_doubles);
+int bnpp_ve_plan_segment_program(bnpp_ve_plan *plan, uint32_t segment, uint32_t *prog, uint64_t prog_cap, uint64_t *prog_words,
+                                 uint32_t *offtab, uint64_t tab_cap, uint64_t *tab_words);
 /* per-launch CUDA-event timing for roofline reports: enable, run, then read
  * ms / algorithmic bytes / union entries / operand count per launch (synchronises). */
 int bnpp_ve_plan_set_profiling(bnpp_ve_plan *plan, int on);

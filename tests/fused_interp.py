@@ -13,7 +13,8 @@ import numpy as np
 from bnpp_b200 import capi, model
 
 HEADER_WORDS, OPERAND_WORDS = 8, 4
-TO_RESULT, WANT_Z = 1, 2
+TO_RESULT, WANT_Z, TO_GLOBAL = 1, 2, 8
+TABLE, GLOBAL = 0xffffffff, 0xfffffffe        # what the high word of a dumped address says it points to
 
 
 class DryPlan:
@@ -64,22 +65,58 @@ class DryPlan:
                                                  tab.ctypes.data_as(capi.c_u32p), tab.size, ctypes.byref(nt)) == 0
         return prog[:np_.value], tab[:nt.value]
 
+    def segments(self, max_steps):
+        """EXPERIMENTAL: cut the plan into fused segments of at most max_steps steps -> list of
+        (first step, end step, lanes, arena doubles, prog, tab)"""
+        L = self.L
+        L.bnpp_ve_plan_set_segments.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32]
+        L.bnpp_ve_plan_segments.argtypes = [ctypes.c_void_p, ctypes.c_uint32, capi.c_u32p, capi.c_u32p, capi.c_u32p,
+                                            ctypes.POINTER(ctypes.c_int32), capi.c_u32p]
+        L.bnpp_ve_plan_segment_program.argtypes = [ctypes.c_void_p, ctypes.c_uint32, capi.c_u32p, ctypes.c_uint64, capi.c_u64p,
+                                                   capi.c_u32p, ctypes.c_uint64, capi.c_u64p]
+        assert L.bnpp_ve_plan_set_segments(self.h, 1, max_steps) == 0
+        n = ctypes.c_uint32()
+        assert L.bnpp_ve_plan_segments(self.h, 0, ctypes.byref(n), None, None, None, None) == 0
+        cap = max(1, n.value)
+        a, b, ar = (ctypes.c_uint32 * cap)(), (ctypes.c_uint32 * cap)(), (ctypes.c_uint32 * cap)()
+        g = (ctypes.c_int32 * cap)()
+        assert L.bnpp_ve_plan_segments(self.h, cap, ctypes.byref(n), a, b, g, ar) == 0
+        out = []
+        for i in range(n.value):
+            np_, nt = ctypes.c_uint64(), ctypes.c_uint64()
+            assert L.bnpp_ve_plan_segment_program(self.h, i, None, 0, ctypes.byref(np_), None, 0, ctypes.byref(nt)) == 0
+            prog = np.zeros(max(1, np_.value), dtype=np.uint32)
+            tab = np.zeros(max(1, nt.value), dtype=np.uint32)
+            assert L.bnpp_ve_plan_segment_program(self.h, i, prog.ctypes.data_as(capi.c_u32p), prog.size, ctypes.byref(np_),
+                                                  tab.ctypes.data_as(capi.c_u32p), tab.size, ctypes.byref(nt)) == 0
+            out.append((a[i], b[i], g[i], ar[i], prog[:np_.value], tab[:nt.value]))
+        return out
+
+    def n_steps(self):
+        vals = [ctypes.c_uint64() for _ in range(5)]
+        assert self.L.bnpp_ve_plan_info(self.h, None, None, None, *[ctypes.byref(v) for v in vals]) == 0
+        return vals[0].value
+
     def close(self):
         if self.h:
             self.L.bnpp_ve_plan_destroy(self.h)
             self.h = None
 
 
-def interpret(prog, tab, n_steps, arena_doubles, tables, ev, result_size):
+def interpret(prog, tab, n_steps, arena_doubles, tables, ev, result_size, glob=None, result=None):
     """one evidence set.  tables: list of 1-D float64 arrays (the resident CPTs); ev: evidence values in the
-    plan's observed order.  -> (result array, partition or None)"""
+    plan's observed order.  glob: {intermediate index: array} -- the plan's global arena, shared by the segments of
+    a launch-per-bucket plan (read for operands made by earlier launches, written by kFusedToGlobal steps).
+    -> (result array, partition or None)"""
     arena = np.full(max(1, arena_doubles), np.nan)
-    result = np.full(max(1, result_size), np.nan)
+    if result is None:
+        result = np.full(max(1, result_size), np.nan)
+    glob = {} if glob is None else glob
     z = None
     pc = 0
     prog = [int(w) for w in prog]
     for _ in range(n_steps):
-        n_out, cx, kf, out_off, tab_off = prog[pc:pc + 5]
+        n_out, cx, kf, out_off, tab_off, dst_lo, dst_hi = prog[pc:pc + 7]
         pc += HEADER_WORDS
         k, flags = kf & 0xff, kf >> 8
         ops = []
@@ -89,8 +126,11 @@ def interpret(prog, tab, n_steps, arena_doubles, tables, ev, result_size):
             kind, nobs = w0 & 0xff, w0 >> 8
             if kind == 0:
                 ops.append((arena, w1, sx))
+            elif w3 == GLOBAL:
+                assert nobs == 0
+                ops.append((glob[w1], 0, sx))      # KeyError: read before any launch wrote it
             else:
-                assert w3 == 0xffffffff
+                assert w3 == TABLE
                 base = 0
                 for j in range(0, nobs, 2):
                     s0, i0, s1, i1 = prog[pc:pc + 4]
@@ -99,7 +139,7 @@ def interpret(prog, tab, n_steps, arena_doubles, tables, ev, result_size):
                     if j + 1 < nobs:
                         base += s1 * ev[i1]
                 ops.append((tables[w1], base, sx))
-        if not flags & TO_RESULT:      # the output of a step never overlaps an arena operand the step still reads
+        if not flags & (TO_RESULT | TO_GLOBAL):      # the output of a step never overlaps an arena operand the step still reads
             for mem, base, sx in ops:
                 if mem is arena:
                     for q2, (m2, b2, s2) in enumerate(ops):
@@ -122,6 +162,9 @@ def interpret(prog, tab, n_steps, arena_doubles, tables, ev, result_size):
             result[out_off:out_off + n_out] = out
             if flags & WANT_Z:
                 z = float(out.sum())
+        elif flags & TO_GLOBAL:
+            assert dst_hi == GLOBAL
+            glob[dst_lo] = out
         else:
             assert out_off + n_out <= arena_doubles
             arena[out_off:out_off + n_out] = out

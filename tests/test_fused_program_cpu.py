@@ -216,3 +216,52 @@ def test_fused_marginals_random_networks():
             p.close()
             checked += 1
     assert checked == 50
+
+
+def test_segment_programs_chain_through_the_global_arena(golden_models, golden_synth):
+    """EXPERIMENTAL (DESIGN gap 4): a plan cut into fused segments of at most m steps -- each reads what earlier
+    segments wrote to the plan's global arena and writes what later ones read -- evaluates to the reference's PR for
+    every cut size; m = 1 is the degenerate case "every step its own launch"."""
+    n = 0
+    for name in ["asia", "child", "alarm", "hepar2", "win95pts"]:
+        m = golden_models[name]
+        cards, scopes, tables = parse_uai(m["uai"])
+        for case in m["pr"]:
+            if not case["flag"]:
+                continue
+            ev = {int(k): v for k, v in case["evidence"].items()}
+            variables = [v for v in range(len(cards)) if v not in ev]
+            order = _order(cards, scopes, variables, ev, case["flag"])
+            observed = sorted(ev)
+            p = DryPlan(cards, scopes, observed, order)
+            for cut in (1, 2, 3, 7, 1000):
+                segs = p.segments(cut)
+                assert segs and segs[0][0] == 0 and segs[-1][1] == p.n_steps()
+                assert all(a[1] == b[0] for a, b in zip(segs, segs[1:])), "every step in exactly one segment"
+                glob, result, z = {}, np.full(1, np.nan), None
+                for first, end, lanes, arena, prog, tab in segs:
+                    assert end - first <= cut and lanes in (32, 128)
+                    res, zz = interpret(prog, tab, end - first, arena, tables, [ev[v] for v in observed], 1, glob=glob, result=result)
+                    z = zz if zz is not None else z
+                assert math.isclose(result[0], case["pr"], rel_tol=REL), (name, case["flag"], cut, result[0])
+                assert z == result[0]
+                if cut == 1000:
+                    assert len(segs) == 1 and not glob          # one segment = the whole plan: nothing goes through global memory
+                n += 1
+            p.close()
+    assert n >= 100
+
+
+def test_segments_of_a_mixed_plan():
+    """a plan with wide steps keeps them as their own launches; the runs of small steps around them become segments"""
+    scopes, _ = synth.random_bn_scopes(40, 24, 3, 3)            # min-fill width 15: buckets from 2^2 to 2^16 entries
+    cards = [2] * 40
+    order = model.elim_order(cards, scopes, list(range(40)), "mf")[0]
+    p = DryPlan(cards, scopes, [], order)
+    assert p.fused_info(1)[0] == 0
+    segs = p.segments(0)
+    steps = p.n_steps()
+    covered = sum(end - first for first, end, *_ in segs)
+    assert segs and 0 < covered < steps
+    assert all(end - first >= 2 for first, end, *_ in segs)
+    p.close()

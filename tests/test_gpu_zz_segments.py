@@ -1,0 +1,64 @@
+"""EXPERIMENTAL, skipped unless BNPP_TEST_EXPERIMENTAL=1 (DESIGN.md gap 4; first device run is the next round's):
+inside a launch-per-bucket plan, every run of consecutive small steps as ONE ve_fused launch.  The host half (the
+segment programs, their traffic through the plan's global arena) is pinned on the CPU by
+tests/test_fused_program_cpu.py::test_segment_programs_chain_through_the_global_arena; this is the device half:
+results bit-identical to the plain launch-per-bucket run, fewer launches."""
+import math
+import os
+
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("BNPP_TEST_EXPERIMENTAL") != "1", reason="experimental path, off by default")]
+
+from bnpp_b200 import synth  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from bnpp_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _pr(bn, ev, flag, segments, cut=0, fused=False):
+    variables = [v for v in range(bn.nvars) if v not in ev]
+    order, _ = bn.order(variables, ev, flag)
+    p = bn.plan(sorted(ev), order)
+    p.set_fused(fused)
+    p.set_segments(segments, cut)
+    bn.ctx.sync()
+    l0 = bn.ctx.launches
+    z, _ = bn.partition(ev, flag)
+    return z, bn.ctx.launches - l0
+
+
+def test_segments_equal_per_bucket(ctx, golden_models):
+    from bnpp_b200 import model
+    for name in ["alarm", "insurance", "Water", "andes", "hepar2"]:
+        m = golden_models[name]
+        bn = model.from_uai_text(ctx, m["uai"])[1]
+        for case in m["pr"]:
+            if not case["flag"]:
+                continue
+            ev = {int(k): v for k, v in case["evidence"].items()}
+            z0, l0 = _pr(bn, ev, case["flag"], False)
+            for cut in (0, 1, 5):
+                z1, l1 = _pr(bn, ev, case["flag"], True, cut)
+                assert z1 == z0, (name, case["flag"], cut, z1, z0)
+                if cut == 0:
+                    assert l1 < l0, (name, l1, l0)
+            assert math.isclose(z0, case["pr"], rel_tol=1e-9)
+        bn.close()
+
+
+def test_segments_on_the_wide_synthetic_network(ctx):
+    """width-22 instance of the config-4 generator: small buckets in segments, wide ones as their own launches"""
+    from bnpp_b200 import model
+    bn = model.from_uai_text(ctx, synth.random_bn_uai(56, 30, 4, 2))[1]
+    z0, l0 = _pr(bn, {}, "mf", False)
+    z1, l1 = _pr(bn, {}, "mf", True)
+    assert z1 == z0 and l1 < l0
+    assert math.isclose(z0, 1.0, rel_tol=1e-9)
+    bn.close()
