@@ -267,7 +267,10 @@ def config5_leg(ctx, steps, warmup, cpu_arm=True):
         cpu = {"error": "%s: %s" % (type(e).__name__, e)}
     return {"metric": "VE PR queries/sec", "value": nsets / ms * 1e3, "unit": "queries/s", "ms_per_batch": ms,
             "config": {"workload": "config 5: %d evidence sets, synthetic BN N=%d W=%d K=%d seed=%d, %d observed ids fixed, "
-                                   "PR per set via VE (min-fill)" % (nsets, N, W, K, seed, nobs)},
+                                   "PR per set via VE (min-fill)" % (nsets, N, W, K, seed, nobs),
+                       "l2_flush": "none: the launch reads 1.3 MB of evidence, 64 KB of CPTs and its 150 KB program and writes "
+                                   "0.5 MB of results; the intermediates stay in shared memory, so this leg is instruction-bound, "
+                                   "not HBM- or L2-bound (profiles/r1_fused_ncu.md)"},
             "e2e": {"value": nsets / e2e_ms * 1e3, "unit": "queries/s", "ms_per_batch": e2e_ms,
                     "h2d_bytes_per_step": host.numel(), "d2h_bytes_per_step": 8 * nsets},
             "gpu_launches_per_batch": launches, "union_entries_per_s": union_entries * nsets / ms * 1e3,
