@@ -61,7 +61,9 @@ def main():
             else:
                 os.environ.pop("BNPP_FUSED_CTAS_PER_SM", None)
             ms, z = timed()
-            out.append({"path": "ve_fused", "lanes": lanes, "ctas_per_sm_cap": ctas or None, "ms_per_batch": ms,
+            used = plan.fused_info(args.sets)[0]          # 0: this setting does not fuse (fell back to one launch per bucket)
+            out.append({"path": "ve_fused" if used else "one launch per bucket (setting refused)", "lanes": lanes,
+                        "ctas_per_sm_cap": ctas or None, "ms_per_batch": ms,
                         "queries_per_s": args.sets / ms * 1e3, "Z": z})
     print(json.dumps(out, indent=1))
 
