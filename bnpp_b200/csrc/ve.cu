@@ -1154,6 +1154,66 @@ int bnpp_ve_plan_fused_info(bnpp_ve_plan *pl, uint32_t nb, int32_t *lanes_per_se
     return BNPP_OK;
 }
 
+// The whole schedule as numbers, for inspection and for the CPU emulator of the tests (tests/plan_emulator.py): what
+// every launch reads and writes and where the intermediates live in the plan's arena.  Stream of uint64 words:
+//   n_factors, n_steps, arena_doubles, result_size,
+//   per factor : src + 1 (0 = intermediate), size, arena_off, rank, rank x (var, card, stride), nobs, nobs x (stride, column)
+//   per step   : elim + 1 (0 = none), out + 1 (0 = the result buffer), roff, want_z, k, k x operand factor,
+//                rank of the output scope, rank x (var, card)
+int bnpp_ve_plan_describe(const bnpp_ve_plan *pl, uint64_t *buf, uint64_t cap, uint64_t *words)
+{
+    if (!pl || !words) return BNPP_EINVAL;
+    std::vector<uint64_t> w;
+    w.push_back(pl->f.size());
+    w.push_back(pl->steps.size());
+    w.push_back(pl->arena_doubles);
+    w.push_back(pl->result_size);
+    for (size_t i = 0; i < pl->f.size(); ++i) {
+        const PlanFactor &pf = pl->f[i];
+        w.push_back((uint64_t)(pf.src + 1));
+        w.push_back(pf.size);
+        w.push_back(i < pl->arena_off.size() ? pl->arena_off[i] : 0);
+        w.push_back(pf.var.size());
+        uint64_t dense = 1;
+        std::vector<uint64_t> st(pf.var.size());
+        for (size_t a = pf.var.size(); a-- > 0;) {
+            st[a] = pf.stride.empty() ? dense : (uint64_t)pf.stride[a];
+            dense *= pf.card[a];
+        }
+        for (size_t a = 0; a < pf.var.size(); ++a) {
+            w.push_back(pf.var[a]);
+            w.push_back(pf.card[a]);
+            w.push_back(st[a]);
+        }
+        w.push_back(pf.obs.size());
+        for (auto &o : pf.obs) {
+            w.push_back((uint64_t)o.first);
+            w.push_back((uint64_t)o.second);
+        }
+    }
+    for (const PlanStep &st : pl->steps) {
+        w.push_back((uint64_t)(st.elim + 1));
+        w.push_back(st.out == -2 ? 0 : (uint64_t)(st.out + 1));
+        w.push_back(st.roff);
+        w.push_back(st.want_z ? 1 : 0);
+        w.push_back(st.operands.size());
+        for (int id : st.operands) w.push_back((uint64_t)id);
+        const std::vector<uint32_t> &ov = st.out == -2 ? st.rvar : pl->f[st.out].var;
+        const std::vector<uint32_t> &oc = st.out == -2 ? st.rcard : pl->f[st.out].card;
+        w.push_back(ov.size());
+        for (size_t a = 0; a < ov.size(); ++a) {
+            w.push_back(ov[a]);
+            w.push_back(oc[a]);
+        }
+    }
+    *words = w.size();
+    if (buf) {
+        if (cap < w.size()) return BNPP_EINVAL;
+        std::copy(w.begin(), w.end(), buf);
+    }
+    return BNPP_OK;
+}
+
 int bnpp_ve_plan_set_segments(bnpp_ve_plan *pl, int on, uint32_t max_steps)
 {
     if (!pl) return BNPP_EINVAL;

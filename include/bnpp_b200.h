@@ -208,6 +208,11 @@ int bnpp_ve_plan_fused_info(bnpp_ve_plan *plan, uint32_t nb, int32_t *lanes_per_
  * Pass NULL buffers to query the sizes.  Works on dry plans (created with ctx == NULL). */
 int bnpp_ve_plan_fused_program(bnpp_ve_plan *plan, uint32_t nb, uint32_t *prog, uint64_t prog_cap, uint64_t *prog_words,
                                uint32_t *offtab, uint64_t tab_cap, uint64_t *tab_words);
+/* The whole schedule as numbers (every launch's operands and output, where each intermediate lives in the plan's
+ * arena), for inspection and for CPU emulation of the HOST logic (bucket schedule, small-table folding, arena
+ * lifetimes) on dry plans; the word stream is documented at the definition in bnpp_b200/csrc/ve.cu.  Pass buf = NULL
+ * to query the size. */
+int bnpp_ve_plan_describe(const bnpp_ve_plan *plan, uint64_t *buf, uint64_t cap, uint64_t *words);
 /* EXPERIMENTAL, off by default (environment BNPP_FUSED_SEGMENTS=1 turns it on for new plans): inside a plan that
  * runs one launch per bucket, every run of consecutive small steps becomes ONE ve_fused launch (single queries);
  * max_steps > 0 cuts the runs into pieces of at most that many steps (tests).  _segments lists the step ranges,

@@ -1,0 +1,111 @@
+"""Host logic of launch-per-bucket plans without a GPU: the schedule a plan dumps (bnpp_ve_plan_describe) is executed
+by the CPU emulator of tests/plan_emulator.py on one flat arena array and must reproduce the reference's PR / MAR
+(golden fixtures) and the oracle's values on wide synthetic networks, where small tables are folded and the arena is
+reused many times over."""
+import math
+
+import numpy as np
+
+from bnpp_b200 import model, synth
+from fused_interp import DryPlan, parse_uai
+from plan_emulator import describe, run
+
+REL = 1e-9
+
+
+def _order(cards, scopes, variables, ev, flag):
+    if not flag:
+        return [v for v in variables if v not in ev]
+    return model.elim_order(cards, scopes, variables, flag, observed=sorted(ev))[0]
+
+
+def test_plan_schedule_partition_golden(golden_models):
+    n = 0
+    for name in ["asia", "child", "alarm", "insurance", "win95pts", "hepar2", "grid3x3"]:
+        m = golden_models[name]
+        cards, scopes, tables = parse_uai(m["uai"])
+        for case in m["pr"]:
+            ev = {int(k): v for k, v in case["evidence"].items()}
+            observed = sorted(ev)
+            order = _order(cards, scopes, [v for v in range(len(cards)) if v not in ev], ev, case["flag"])
+            p = DryPlan(cards, scopes, observed, order)
+            res, z = run(describe(p.h), tables, [ev[v] for v in observed])
+            assert math.isclose(res[0], case["pr"], rel_tol=REL), (name, case["flag"], res[0], case["pr"])
+            assert z is not None and math.isclose(z, res[0], rel_tol=1e-15)
+            p.close()
+            n += 1
+    assert n >= 40
+
+
+def test_plan_schedule_marginals_golden(golden_models):
+    for name in ["asia", "child", "alarm", "network"]:
+        m = golden_models[name]
+        cards, scopes, tables = parse_uai(m["uai"])
+        for case in m["mar"][:2]:
+            ev = {int(k): v for k, v in case["evidence"].items()}
+            observed = sorted(ev)
+            order = _order(cards, scopes, [v for v in range(len(cards)) if v not in ev], ev, "mf")
+            p = DryPlan(cards, scopes, observed, order, marginals=True)
+            off, size, total = p.layout
+            res, _ = run(describe(p.h), tables, [ev[v] for v in observed])
+            for v, want in enumerate(case["mar"]):
+                seg = res[off[v]:off[v] + size[v]]
+                got = np.array([1.0]) if size[v] == 1 else seg / seg.sum()
+                assert np.allclose(got, want, rtol=REL, atol=1e-300), (name, v)
+            p.close()
+
+
+def test_plan_schedule_wide_network_with_folding_and_arena_reuse(golden_synth):
+    """the config-4 generator at reduced width (tables up to 2^21 entries: small tables are folded ahead of the wide
+    launches, arena slots are reused): PR against the compiled reference's value, and Z = 1 without evidence"""
+    done = 0
+    for rec in golden_synth["bn"]:
+        if rec["N"] > 48:
+            continue
+        cards, scopes, tables = parse_uai(synth.random_bn_uai(rec["N"], rec["W"], rec["K"], rec["seed"]))
+        ev = {int(k): v for k, v in rec["evidence"].items()}
+        observed = sorted(ev)
+        for case in rec["cases"]:
+            if "pr" not in case and ev:
+                continue
+            order = _order(cards, scopes, [v for v in range(len(cards)) if v not in ev], ev, case["flag"])
+            p = DryPlan(cards, scopes, observed, order)
+            d = describe(p.h)
+            widest = max(int(np.prod([c for _, c in st["scope"]])) for st in d["steps"])
+            if widest > (1 << 21):
+                p.close()
+                continue
+            res, _ = run(d, tables, [ev[v] for v in observed])
+            want = case.get("pr", 1.0)
+            assert math.isclose(res[0], want, rel_tol=REL), (rec["N"], case["flag"], res[0], want)
+            # the arena is smaller than the sum of the intermediates: slots are reused
+            assert d["arena"] < sum(f["size"] for f in d["factors"] if f["src"] < 0)
+            p.close()
+            done += 1
+    assert done >= 2
+
+
+def test_plan_schedule_with_small_table_folding():
+    """width 22 (2^23-entry union tables): ahead of a wide launch the plan multiplies the bucket's small CPTs into one
+    table and copies raw input views into canonical axis order (fold_small, ve.cu) -- product-only steps that the
+    emulator executes like any other; a normalised BN must come out at Z = 1, and P(x=0) + P(x=1) = 1 for a leaf"""
+    cards, scopes, tables = parse_uai(synth.random_bn_uai(56, 30, 4, 2))
+    n = len(cards)
+    order, width = model.elim_order(cards, scopes, list(range(n)), "mf")
+    assert 18 <= width <= 26
+    p = DryPlan(cards, scopes, [], order)
+    d = describe(p.h)
+    folds = [st for st in d["steps"] if st["elim"] < 0 and st["out"] >= 0]
+    assert folds, "no product-only step: the plan did not fold anything"
+    res, _ = run(d, tables, [])
+    assert math.isclose(res[0], 1.0, rel_tol=REL)
+    assert d["arena"] < sum(f["size"] for f in d["factors"] if f["src"] < 0)
+    p.close()
+    leaf = n - 1
+    order1, _ = model.elim_order(cards, scopes, [v for v in range(n) if v != leaf], "mf", observed=[leaf])
+    p = DryPlan(cards, scopes, [leaf], order1)
+    d = describe(p.h)
+    z0, _ = run(d, tables, [0])
+    z1, _ = run(d, tables, [1])
+    assert math.isclose(z0[0] + z1[0], 1.0, rel_tol=REL)
+    p.close()
