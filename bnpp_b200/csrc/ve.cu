@@ -857,6 +857,53 @@ int run_fused(bnpp_ve_plan *pl, FusedProgram &fp, int G, const double *const *ta
     return fused_launch(ctx, G, p);
 }
 
+// Segments want long runs of small steps, a min-fill order interleaves small buckets with wide ones.  Any
+// topological order of the steps gives the same numbers (operand lists are untouched), so: first every small step all
+// of whose inputs are CPTs or outputs of such steps, in their old relative order, then the rest in theirs (the result
+// step stays last).  The arena is laid out again for the new lifetimes.  Only before the first run of a PR plan.
+void reorder_small_first(bnpp_ve_plan *pl)
+{
+    if (pl->is_mar || pl->runs || pl->arena || pl->steps.size() < 3) return;
+    const size_t ns = pl->steps.size();
+    std::vector<int> producer(pl->f.size(), -1);
+    for (size_t s = 0; s < ns; ++s)
+        if (pl->steps[s].out >= 0) producer[pl->steps[s].out] = (int)s;
+    std::vector<char> early(ns, 0);
+    size_t n_early = 0;
+    for (size_t s = 0; s < ns; ++s) {
+        const PlanStep &st = pl->steps[s];
+        bool e = st.out >= 0 && st.union_entries <= kFusedMaxUnion && !st.operands.empty() && (int)st.operands.size() <= kMaxK;
+        for (int id : st.operands)
+            if (e && pl->f[id].src < 0) e = producer[id] >= 0 && producer[id] < (int)s && early[producer[id]];
+        early[s] = e;
+        n_early += e;
+    }
+    if (n_early == 0 || n_early == ns) return;
+    std::vector<PlanStep> steps;
+    steps.reserve(ns);
+    for (int pass = 1; pass >= 0; --pass)
+        for (size_t s = 0; s < ns; ++s)
+            if (early[s] == pass) steps.push_back(std::move(pl->steps[s]));
+    pl->steps = std::move(steps);
+    for (PlanFactor &pf : pl->f) pf.last_use = -1;
+    uint64_t live = 0;
+    pl->peak_bytes = 0;
+    for (size_t s = 0; s < ns; ++s)
+        for (int id : pl->steps[s].operands) pl->f[id].last_use = (int)s;
+    for (size_t s = 0; s < ns; ++s) {
+        const PlanStep &st = pl->steps[s];
+        if (st.out >= 0) live += 8 * pl->f[st.out].size;
+        pl->peak_bytes = std::max(pl->peak_bytes, live);
+        for (int id : st.operands)
+            if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) live -= 8 * pl->f[id].size;
+    }
+    pl->arena_doubles = 0;
+    build_exec(pl);
+    pl->exec.clear();
+    pl->exec_planned.clear();
+    pl->fused = FusedProgram();
+}
+
 }  // namespace
 
 extern "C" {
@@ -930,6 +977,7 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
             if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) live -= 8 * pl->f[id].size;
     }
     build_exec(pl);
+    if (pl->segments_mode) reorder_small_first(pl);
     *out = pl;
     return BNPP_OK;
 }
@@ -1217,6 +1265,7 @@ int bnpp_ve_plan_describe(const bnpp_ve_plan *pl, uint64_t *buf, uint64_t cap, u
 int bnpp_ve_plan_set_segments(bnpp_ve_plan *pl, int on, uint32_t max_steps)
 {
     if (!pl) return BNPP_EINVAL;
+    if (on) reorder_small_first(pl);
     pl->segments_mode = on != 0;
     pl->segments_max_steps = max_steps;
     pl->segments_built = false;
