@@ -17,8 +17,8 @@ from fused_interp import DryPlan, parse_uai  # noqa: E402
 
 SMALL = 1 << 14
 print("| network | variables | min-fill width | order ms (host, this container) | plan ms (host) | launches | small launches | share of union entries in small steps | "
-      "K9 today | launches if small runs fused |")
-print("|---|---:|---:|---:|---:|---:|---:|---:|---|---:|")
+      "K9 today | launches if small runs fused (elimination order) | launches, segment builder (small steps first) |")
+print("|---|---:|---:|---:|---:|---:|---:|---:|---|---:|---|")
 for path in sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", "models", "bayesnets", "*.uai"))):
     cards, scopes, _ = parse_uai(open(path).read())
     n = len(cards)
@@ -47,7 +47,13 @@ for path in sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", "models", "bay
     after = (ns - sum(small)) + runs
     tot = sum(ent) or 1
     lanes = p.fused_info(1)[0]
-    print("| %s | %d | %d | %.2f | %.2f | %d | %d | %.1f %% | %s | %d |"
+    built = "-"
+    if not lanes:
+        q = DryPlan(cards, scopes, [], order)
+        segs = q.segments(0)           # what the (experimental) segment builder makes of it, small steps first
+        built = "%d (%d segments)" % (q.n_steps() - sum(e - a for a, e, *_ in segs) + len(segs), len(segs))
+        q.close()
+    print("| %s | %d | %d | %.2f | %.2f | %d | %d | %.1f %% | %s | %d | %s |"
           % (os.path.basename(path)[:-4], n, width, (t1 - t0) * 1e3, (t2 - t1b) * 1e3, ns, sum(small),
-             100.0 * sum(e for e, s in zip(ent, small) if s) / tot, ("one launch, %d lanes" % lanes) if lanes else "per bucket", 1 if lanes else after))
+             100.0 * sum(e for e, s in zip(ent, small) if s) / tot, ("one launch, %d lanes" % lanes) if lanes else "per bucket", 1 if lanes else after, built))
     p.close()
