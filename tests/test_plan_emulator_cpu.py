@@ -148,3 +148,27 @@ def test_small_first_reordering_keeps_results_and_lengthens_segments(golden_mode
         after = len(d["steps"]) - sum(e - a for a, e, *_ in segs) + len(segs)
         assert after <= before, (name, before, after)          # (shipped networks: Munin1 50 -> 40, Diabetes 276 -> 254 launches)
         p.close()
+
+
+def test_plan_schedule_shrinks_buckets_with_many_factors():
+    """a hub variable in 12 factors, eliminated first: the bucket exceeds BNPP_MAX_OPERANDS, the plan multiplies the
+    smallest tables together first (shrink, ve.cu) -- same value as the oracle's one-by-one products"""
+    import oracle as orc
+    rng = np.random.default_rng(3)
+    n = 12
+    cards = [3] + [2] * (n - 1)
+    scopes = [[0]] + [[0, i] for i in range(1, n)] + [[i, i + 1] for i in range(1, n - 1)]
+    tables = [rng.uniform(0.1, 1.5, int(np.prod([cards[v] for v in sc]))) for sc in scopes]
+    m = orc.OModel("MARKOV", cards, [orc.OFactor(sc, t) for sc, t in zip(scopes, tables)])
+    for ev in ({}, {5: 1}):
+        order = [v for v in range(n) if v not in ev]            # the hub first
+        want = orc.partition(m, ev, order)
+        observed = sorted(ev)
+        p = DryPlan(cards, scopes, observed, order)
+        p.set_fused(False)
+        d = describe(p.h)
+        assert max(len(st["ops"]) for st in d["steps"]) <= 6
+        assert any(st["elim"] < 0 and st["out"] >= 0 for st in d["steps"]), "no product-only step: nothing was shrunk"
+        res, _ = run(d, tables, [ev[v] for v in observed])
+        assert math.isclose(res[0], want, rel_tol=1e-12), (ev, res[0], want)
+        p.close()
