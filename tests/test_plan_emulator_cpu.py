@@ -172,3 +172,41 @@ def test_plan_schedule_shrinks_buckets_with_many_factors():
         res, _ = run(d, tables, [ev[v] for v in observed])
         assert math.isclose(res[0], want, rel_tol=1e-12), (ev, res[0], want)
         p.close()
+
+
+def test_plan_schedule_random_networks():
+    """random mixed-cardinality factor sets, random evidence, every heuristic: the dumped schedule on the flat arena
+    against the oracle's bucket elimination -- with segments off and on (re-ordered steps, arena laid out again)"""
+    import random
+    import oracle as orc
+    rng = random.Random(4242)
+    checked = 0
+    for trial in range(40):
+        n = rng.randint(4, 14)
+        cards = [rng.randint(2, 4) for _ in range(n)]
+        scopes, tables = [], []
+        for _ in range(rng.randint(n, 2 * n + 3)):
+            sc = rng.sample(range(n), rng.randint(1, min(4, n)))
+            scopes.append(sc)
+            tables.append(np.array([rng.uniform(0.05, 2.0) for _ in range(int(np.prod([cards[v] for v in sc])))]))
+        ev = {v: rng.randrange(cards[v]) for v in rng.sample(range(n), rng.randint(0, n // 3))}
+        m = orc.OModel("MARKOV", cards, [orc.OFactor(sc, t) for sc, t in zip(scopes, tables)])
+        observed = sorted(ev)
+        variables = [v for v in range(n) if v not in ev]
+        for flag in ("", "mf", "md", "wmf"):
+            order = _order(cards, scopes, variables, ev, flag)
+            want = orc.partition(m, ev, order)
+            for segments in (False, True):
+                p = DryPlan(cards, scopes, observed, order)
+                if segments:
+                    p.segments(0)
+                d = describe(p.h)
+                if not d["steps"] or d["steps"][-1]["out"] >= 0:      # nothing left to multiply: the result is the scalar 1
+                    assert math.isclose(want, 1.0, rel_tol=1e-12) or not d["steps"]
+                    p.close()
+                    continue
+                res, _ = run(d, tables, [ev[v] for v in observed])
+                assert math.isclose(res[0], want, rel_tol=1e-12), (trial, flag, segments, res[0], want)
+                p.close()
+                checked += 1
+    assert checked >= 250
