@@ -25,7 +25,19 @@ EXPORTS = [
     "bnpp_fg_marginals", "bnpp_elim_order", "bnpp_order_width", "bnpp_ve_plan_create", "bnpp_ve_plan_destroy",
     "bnpp_ve_plan_info", "bnpp_ve_plan_run", "bnpp_ve_plan_run_batched", "bnpp_ve_plan_set_profiling",
     "bnpp_ve_plan_step_stats", "bnpp_ve_plan_step_kernel", "bnpp_ve_plan_set_fused", "bnpp_ve_plan_fused_info", "bnpp_ve_plan_fused_program", "bnpp_ve_plan_describe", "bnpp_ve_plan_set_segments", "bnpp_ve_plan_segments", "bnpp_ve_plan_segment_program", "bnpp_mar_plan_create", "bnpp_mar_plan_layout", "bnpp_pick_shard_vars",
+    "bnpp_tuning_set", "bnpp_tuning_get",
 ]
+
+
+def tuning_set(key, value):
+    """process-wide kernel-selection knob (bnpp_tuning_set); returns the previous value"""
+    L = lib()
+    L.bnpp_tuning_set.argtypes = [ctypes.c_char_p, ctypes.c_uint64]
+    L.bnpp_tuning_get.argtypes = [ctypes.c_char_p, c_u64p]
+    old = ctypes.c_uint64()
+    if L.bnpp_tuning_get(key.encode(), ctypes.byref(old)) != 0 or L.bnpp_tuning_set(key.encode(), int(value)) != 0:
+        raise BnppError(-1, "unknown tuning key %r" % key)
+    return old.value
 
 
 class Scope(ctypes.Structure):

@@ -32,6 +32,7 @@
 
 #include "common.cuh"
 #include "contract.hpp"
+#include "contract_mv.hpp"
 
 namespace bnpp {
 
@@ -733,7 +734,11 @@ std::string LaunchDesc::name()
 {
     const ParamsHead &h = head();
     char nm[128];
-    if (generic) snprintf(nm, sizeof nm, "contract_generic<%s,K=%d,div=%d> cx=%u R=%u", variant, k, div, h.cx, R);
+    if (mvt) snprintf(nm, sizeof nm, "contract_mvt<%s,K=%d,stages=%d> cx=%u T=%u g=%u tiles=%u R=%u stage=%uB", variant, k, U, h.cx,
+                      mvtp.T, mvtp.g, mvtp.n_tiles, R, mvtp.stage_doubles * 8u);
+    else if (mv) snprintf(nm, sizeof nm, "contract_mv<%s,K=%d,U=%d> cx=%u T=%u E=%u g=%u tiles=%u R=%u", variant, k, U, h.cx, mvp.T, mvp.E,
+                     mvp.g, mvp.n_tiles, R);
+    else if (generic) snprintf(nm, sizeof nm, "contract_generic<%s,K=%d,div=%d> cx=%u R=%u", variant, k, div, h.cx, R);
     else snprintf(nm, sizeof nm, "contract_fast<%s,K=%d,C=%d,V=%d,U=%d,div=%d> R=%u cls=%d,%d,%d", variant, k, C, V, U, div, R,
                   h.cls[0], k > 1 ? h.cls[1] : -1, k > 2 ? h.cls[2] : -1);
     return nm;
@@ -798,8 +803,8 @@ int contract_launch(bnpp_ctx *ctx, LaunchDesc &d, const double *const *in, doubl
     h.out = out;
     h.z = z;
     void *args[1];
-    args[0] = d.p2 ? (d.staged ? static_cast<void *>(&d.p2p) : static_cast<void *>(&d.p2p.b)) : static_cast<void *>(&d.mrp);
-    BNPP_CUDA(ctx, cudaLaunchKernel(d.fn, dim3(d.grid), dim3(kBlock), args, 0, ctx->stream));
+    args[0] = d.params();
+    BNPP_CUDA(ctx, cudaLaunchKernel(d.fn, dim3(d.grid), dim3(kBlock), args, d.smem, ctx->stream));
     ctx->launches++;
     ctx->last_desc = &d;
     ctx->last_kernel.clear();
@@ -819,6 +824,7 @@ int contract(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *ou
     const int rc2 = contract_launch(ctx, d, in, out_dev, z_dev);
     ctx->last_kernel = d.name();      // the descriptor dies here: keep the printable name, not the pointer
     ctx->last_desc = nullptr;
+    contract_release(ctx, d);         // stream-ordered: after the launch that reads the table
     return rc2;
 }
 
@@ -1003,6 +1009,33 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
     }
 
     const bool generic = (cx > 2);
+    if (generic && !divide && n_out * cx >= mv_min_entries()) {
+        // multi-valued elimination: the table-driven tile kernel (contract_mv.cu), in the output's own axis order
+        std::vector<MVAxis> mva;
+        for (int i = 0; i < wr; ++i) {
+            if (axes[i].ext <= 1) continue;
+            MVAxis a;
+            a.ext = axes[i].ext;
+            for (int q = 0; q < kMaxK; ++q) a.s[q] = axes[i].s[q];
+            mva.push_back(a);
+        }
+        ParamsHead hm;
+        memset(&hm, 0, sizeof hm);
+        for (int q = 0; q < k; ++q) hm.in[q] = ops[q].data;
+        hm.out = out_dev;
+        hm.partials = ctx->partials;
+        hm.ticket = ctx->ticket;
+        hm.z = z_dev;
+        hm.status = ctx->status;
+        *desc = LaunchDesc();
+        if (mv_staged_enabled()) {
+            const int rct = plan_mvt(ctx, desc, k, cx, sx, op_bytes, mva, n_out, hm);
+            if (rct <= 0) return rct;
+            *desc = LaunchDesc();
+        }
+        const int rc = plan_mv(ctx, desc, k, cx, sx, op_bytes, mva, n_out, hm);
+        if (rc <= 0) return rc;     // planned, or an error; 1 = not applicable: the one-entry-per-thread kernel below
+    }
     const int C = generic ? 0 : (int)cx;
     int V = 1;
     if (!generic && !m.empty() && (m.back().ext % 2 == 0)) V = 2;

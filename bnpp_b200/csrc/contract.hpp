@@ -65,21 +65,67 @@ struct ParamsP2S {
     StageInfo st;
 };
 
+// Multi-valued elimination (cardinality of the eliminated variable > 2), table driven.  A CTA owns TILES of T
+// consecutive output entries = [g digits of the split axis] x [all inner axes]; the E = T * cx union entries of a
+// tile are enumerated lane by lane in the order that is contiguous in the large operands (the eliminated variable
+// fastest when it is their stride-1 axis), their products go to a shared-memory stage with an odd row pitch, and
+// one thread per output entry adds its row up in the reference's order.  What depends on the position INSIDE a
+// tile is the same for every tile and comes from a table built once by the plan (device copy `tab`, staged into
+// shared memory by one bulk copy per CTA): per entry the operand offsets and the stage slot.  What depends on the
+// tile is a mixed-radix decomposition of the tile index over the outer axes, done by K+1 threads per tile.
+struct ParamsMV {
+    ParamsHead h;               // in / out / z / partials / ticket / status, cx; n_items = output entries
+    const uint32_t *tab;        // [E][KP] words: operand offsets..., (stage slot | tile-local output index << 16) in the last word
+    uint32_t E, T, cxp;         // union entries and output entries of a full tile, row pitch of the stage (odd)
+    uint32_t inner;             // output entries per digit of the split axis
+    uint32_t g, ext_split, n_split;   // split axis: digits per tile, extent, tiles along it
+    uint32_t n_tiles, R;        // R outer axes (outside the split axis), outermost first
+    FastDiv dsplit;             // tile -> (outer index, chunk of the split axis); valid when n_split >= 2
+    FastDiv div[kMaxR];
+    uint32_t s_split[kMaxK];    // operand stride of the split axis
+    uint32_t s[kMaxK][kMaxR];   // operand stride per outer axis
+};
+
+// Multi-valued elimination, TMA-staged (contract_mvt.cu): per tile every operand is ONE contiguous range brought
+// into shared memory by a bulk copy; thread j owns output entry j of the tile.
+constexpr int kMvtMaxStages = 6;
+struct ParamsMVT {
+    ParamsHead h;               // in / out / z / partials / ticket / status, cx, sx; n_items = output entries
+    const uint32_t *rowtab;     // [T][K]: offset of output entry j's row inside operand k's range
+    uint32_t T, inner;          // output entries per tile, output entries per digit of the split axis
+    uint32_t g, ext_split, n_split;
+    uint32_t n_tiles, R;
+    uint32_t stages, stage_doubles, rowtab_bytes;
+    uint32_t range[kMaxK];      // doubles of operand k one tile touches (a contiguous range)
+    uint32_t soff[kMaxK];       // where operand k's range sits inside a stage (doubles, even)
+    FastDiv dsplit;
+    FastDiv div[kMaxR];
+    uint32_t s_split[kMaxK];
+    uint32_t s[kMaxK][kMaxR];
+};
+
 struct LaunchDesc {
     const void *fn = nullptr;
     unsigned grid = 0;
     bool p2 = false;
     bool staged = false;
+    bool mv = false;            // contract_mv: params in mvp, dynamic shared memory `smem`, device table `mv_tab`
+    bool mvt = false;           // contract_mvt: params in mvtp, same ownership of `mv_tab`
     int k = 0;
+    unsigned smem = 0;
+    uint32_t *mv_tab = nullptr; // owned: freed by contract_release (stream-ordered)
     ParamsP2S p2p;              // .b is the plain power-of-two block
     ParamsMR mrp;
+    ParamsMV mvp;
+    ParamsMVT mvtp;
     // pieces of the printable name (formatted lazily: a VE query launches hundreds of these)
     const char *variant = "";
     int C = 0, V = 0, U = 0;
     bool div = false, generic = false;
     uint32_t R = 0;
     std::string name();
-    ParamsHead &head() { return p2 ? p2p.b.h : mrp.h; }
+    ParamsHead &head() { return mvt ? mvtp.h : (mv ? mvp.h : (p2 ? p2p.b.h : mrp.h)); }
+    void *params() { return mvt ? static_cast<void *>(&mvtp) : mv ? static_cast<void *>(&mvp) : (p2 ? (staged ? static_cast<void *>(&p2p) : static_cast<void *>(&p2p.b)) : static_cast<void *>(&mrp)); }
 };
 
 int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope, int64_t elim_var,
@@ -87,5 +133,7 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
 // in / out / z replace the pointers the descriptor was planned with; they must be at least as
 // aligned (a descriptor planned for 32-byte aligned operands may use 256-bit loads)
 int contract_launch(bnpp_ctx *ctx, LaunchDesc &desc, const double *const *in, double *out, double *z);
+// frees what a descriptor owns on the device (the table of a contract_mv launch); stream-ordered, idempotent
+void contract_release(bnpp_ctx *ctx, LaunchDesc &desc);
 
 }  // namespace bnpp

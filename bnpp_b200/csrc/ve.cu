@@ -1139,6 +1139,10 @@ int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
     if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
     if (pl->graph) cudaGraphDestroy(pl->graph);
     if (pl->arena) bnpp_free(pl->ctx, pl->arena);
+    for (LaunchDesc &d : pl->exec) contract_release(pl->ctx, d);
+    if (pl->ctx && pl->ctx->last_desc && !pl->exec.empty() && pl->ctx->last_desc >= (void *)&pl->exec.front() &&
+        pl->ctx->last_desc <= (void *)&pl->exec.back())
+        pl->ctx->last_desc = nullptr;       // bnpp_last_launch must not follow a pointer into a dead plan
     for (auto &seg : pl->segs) {
         if (seg.prog.prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(seg.prog.prog_dev));
         if (seg.prog.offtab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(seg.prog.offtab_dev));
@@ -1496,12 +1500,13 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             h.out = dst;
             h.z = z;
             void *args[1];
-            args[0] = d.p2 ? (d.staged ? static_cast<void *>(&d.p2p) : static_cast<void *>(&d.p2p.b)) : static_cast<void *>(&d.mrp);
+            args[0] = d.params();
             cudaKernelNodeParams kp;
             memset(&kp, 0, sizeof kp);
             kp.func = const_cast<void *>(d.fn);
             kp.gridDim = dim3(d.grid);
             kp.blockDim = dim3(kBlock);
+            kp.sharedMemBytes = d.smem;
             kp.kernelParams = args;
             cudaError_t e;
             if (fresh) e = cudaGraphAddKernelNode(&pl->nodes[s], pl->graph, s ? &pl->nodes[s - 1] : nullptr, s ? 1 : 0, &kp);

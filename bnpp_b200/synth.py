@@ -83,3 +83,24 @@ def _emit(header, card, scopes, tables):
     for t in tables:
         out.append("%d %s" % (len(t), " ".join("%.17g" % v for v in t)))
     return "\n".join(out) + "\n"
+
+
+# config 4 per GPU count: generator parameters (N, W, K, seed) and how many leaves are observed.  Chosen with the host
+# orderer so that the min-fill width is 27 + log2(G) and fixing the log2(G) shard variables leaves every rank a
+# width-27 problem of ~2.0-2.2e9 union entries.  The 1-GPU network has six leaves only and observing more than four
+# of them tips a min-fill tie into a width-29 order, hence 4 there.
+WIDE = {1: (64, 40, 4, 5, 4), 2: (68, 40, 4, 27, 8), 4: (72, 40, 4, 23, 8), 8: (76, 44, 4, 3, 8)}
+# the strong-scaling network: ONE fixed network (the 8-GPU one, min-fill width 30) at every GPU count
+STRONG = WIDE[8]
+
+
+def wide_bn(key):
+    """-> (N, W, K, seed, evidence) of config 4: `key` is a GPU count of WIDE or the string "strong".
+    evidence = observed leaves (variables that are nobody's parent) with values from Random(seed + 100)."""
+    N, W, K, seed, nobs = STRONG if key == "strong" else WIDE[key]
+    scopes, _ = random_bn_scopes(N, W, K, seed)
+    parents = set(v for sc in scopes for v in sc[1:])
+    leaves = [v for v in range(N) if v not in parents]
+    rng = random.Random(seed + 100)
+    obs = sorted(rng.sample(leaves, min(nobs, len(leaves))))
+    return N, W, K, seed, {v: rng.randrange(2) for v in obs}

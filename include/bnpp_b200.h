@@ -78,6 +78,16 @@ uint64_t bnpp_launch_count(const bnpp_ctx *ctx);
 /* name, grid and block of the most recent contraction launch (diagnostics / tests) */
 int bnpp_last_launch(const bnpp_ctx *ctx, char *name, size_t name_len, uint32_t *grid, uint32_t *block);
 
+/* Kernel-selection knobs, process wide (tests and profiling; the defaults are the product):
+ *   "mv_min_entries" : union entries from which an elimination of a variable with > 2 values takes the tiled
+ *                      multi-valued kernel (contract_mv; default 2^15, 0 = always)
+ *   "mv_emax"        : union entries per tile of the gather variant of that kernel (64..2048; 0 = default)
+ *   "mv_staged"      : 1 (default) = operands whose tile footprint is a compact range are staged in shared memory
+ *                      by bulk copies (contract_mvt); 0 = always the gather variant (contract_mv)
+ * Unknown keys return BNPP_EINVAL.  Environment BNPP_MV_MIN_ENTRIES / BNPP_MV_EMAX seed the defaults. */
+int bnpp_tuning_set(const char *key, uint64_t value);
+int bnpp_tuning_get(const char *key, uint64_t *value);
+
 int bnpp_alloc(bnpp_ctx *ctx, uint64_t n_doubles, double **dptr);     /* stream-ordered pool */
 int bnpp_free(bnpp_ctx *ctx, double *dptr);
 int bnpp_upload(bnpp_ctx *ctx, double *dst_dev, const double *src_host, uint64_t n);   /* async if src is pinned */

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--only", default=None, help="kind filter")
     ap.add_argument("--no-reverse", action="store_true")
     ap.add_argument("--mixed", action="store_true", help="the mixed-cardinality case of SURVEY 8d: cards cycle 2,3,4,5 over 16 axes (2.07e8 union entries)")
+    ap.add_argument("--mv", default=None, help="multi-valued elimination: comma-separated cardinalities of the eliminated variable, e.g. 3,4,5,7,8")
     args = ap.parse_args()
     ctx = capi.Context(0)
     peak, how = peak_gbs()
@@ -67,6 +68,43 @@ def main():
         return cache[key]
 
     rows = []
+    if args.mv:
+        # multi-valued elimination (contract_mv): A over 13 axes of 4 values + the eliminated variable innermost
+        # (the canonical VE layout), B the same minus two axes, >= 2^27 union entries
+        for cx in [int(c) for c in args.mv.split(",")]:
+            nax = 13
+            cards = [4] * nax + [cx]
+            sa = list(range(nax + 1))
+            sb = [v for v in sa if v not in (3, 9)]
+            A = DeviceFactor.empty(ctx, sa, [cards[v] for v in sa])
+            B = DeviceFactor.empty(ctx, sb, [cards[v] for v in sb])
+            A.buf[:-1] = torch.rand(A.size, generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+            B.buf[:-1] = torch.rand(B.size, generator=g, device="cuda", dtype=torch.float64) * 0.9 + 0.1
+            out_scope = sa[:-1]
+            out = DeviceFactor.empty(ctx, out_scope, [cards[v] for v in out_scope])
+            for k_ops, ops in ((1, [(A.ptr, sa, A.cards, None)]), (2, [(A.ptr, sa, A.cards, None), (B.ptr, sb, B.cards, None)])):
+                torch.cuda.synchronize()
+                s_ = ctx.torch_stream
+                times = []
+                for it in range(args.iters + 2):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(s_)
+                    ctx.product_sum_out(ops, out_scope, out.cards, nax, out.ptr, out.zptr)
+                    e1.record(s_)
+                    e1.synchronize()
+                    if it >= 2:
+                        times.append(e0.elapsed_time(e1))
+                ms = sum(times) / len(times)
+                nbytes = 8 * (A.size + (B.size if k_ops == 2 else 0) + out.size)
+                print("mv  cx=%2d K=%d  %.3e entries  %8.3f ms  %8.1f GB/s  %5.1f%% of %s peak  %.3e entries/s  %s"
+                      % (cx, k_ops, A.size, ms, nbytes / ms / 1e6, 100 * nbytes / ms / 1e6 / peak, how, A.size / ms * 1e3,
+                         ctx.last_launch()[0]), flush=True)
+                rows.append({"kind": "mv", "card": cx, "k": k_ops, "entries": A.size, "ms": ms, "GBs": nbytes / ms / 1e6,
+                             "frac": nbytes / ms / 1e6 / peak, "kernel": ctx.last_launch()[0]})
+            del A, B, out
+        if args.json:
+            json.dump({"peak_gbs": peak, "peak_kind": how, "rows": rows}, open(args.json, "w"), indent=1)
+        return
     if args.mixed:
         cards = [2, 3, 4, 5] * 4
         allv = list(range(16))
