@@ -202,23 +202,41 @@ __global__ void __launch_bounds__(kBlock) contract_batched_bin(const __grid_cons
     }
 }
 
-// [nb][n_obs] (one row per evidence set, as the caller has it) -> [n_obs][nb]
-__global__ void transpose_evidence(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint32_t nb, uint32_t n_obs)
+// [nb][n_obs] (one row per evidence set, as the caller has it) -> [n_obs][nb] (transpose != 0) or a copy in place
+// order.  A value outside its variable's cardinality would move a CPT view past its table: it is replaced by 0 and
+// BNPP_STATUS_BAD_EVIDENCE is raised (the reference throws from Factor::operator[] there, code/factor.cpp:83-95).
+__global__ void sanitize_evidence(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, uint32_t nb, uint32_t n_obs,
+                                  const uint32_t *__restrict__ card, int transpose, unsigned int *status)
 {
     const uint64_t n = (uint64_t)nb * n_obs;
+    bool bad = false;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t j = (uint32_t)(i / nb), b = (uint32_t)(i - (uint64_t)j * nb);
-        out[i] = in[(uint64_t)b * n_obs + j];
+        uint32_t j, b;
+        if (transpose) {
+            j = (uint32_t)(i / nb);
+            b = (uint32_t)(i - (uint64_t)j * nb);
+        } else {
+            b = (uint32_t)(i / n_obs);
+            j = (uint32_t)(i - (uint64_t)b * n_obs);
+        }
+        uint8_t v = in[(uint64_t)b * n_obs + j];
+        if (v >= card[j]) {
+            bad = true;
+            v = 0;
+        }
+        out[i] = v;
     }
+    if (bad) atomicOr(status, BNPP_STATUS_BAD_EVIDENCE);
 }
 
-int transpose_evidence_launch(bnpp_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t nb, uint32_t n_obs)
+int sanitize_evidence_launch(bnpp_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t nb, uint32_t n_obs, const uint32_t *card_dev,
+                             bool transpose)
 {
     if (!nb || !n_obs) return BNPP_OK;
     const uint64_t n = (uint64_t)nb * n_obs;
     uint64_t blocks = (n + 255) / 256;
     if (blocks > 4096) blocks = 4096;
-    transpose_evidence<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, nb, n_obs);
+    sanitize_evidence<<<(unsigned)blocks, 256, 0, ctx->stream>>>(in, out, nb, n_obs, card_dev, transpose ? 1 : 0, ctx->status);
     BNPP_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return BNPP_OK;

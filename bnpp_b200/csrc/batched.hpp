@@ -23,7 +23,9 @@ int contract_batched_step(bnpp_ctx *ctx, int k, const BatchedOperandDesc *ops, c
                           uint32_t ev_stride, uint32_t n_obs, double *out_dev, std::vector<uint32_t> *offtab_host,
                           uint32_t **offtab_dev);
 // ev_dev above is COLUMN-major ([n_obs][ev_stride], first set of the slice at ev_dev[0]); this turns the
-// caller's row-major [nb][n_obs] matrix into it
-int transpose_evidence_launch(bnpp_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t nb, uint32_t n_obs);
+// caller's row-major [nb][n_obs] matrix into it (transpose) or copies it, replacing values outside their
+// variable's cardinality (card_dev[n_obs]) by 0 and raising BNPP_STATUS_BAD_EVIDENCE
+int sanitize_evidence_launch(bnpp_ctx *ctx, const uint8_t *in, uint8_t *out, uint32_t nb, uint32_t n_obs, const uint32_t *card_dev,
+                             bool transpose);
 
 }  // namespace bnpp

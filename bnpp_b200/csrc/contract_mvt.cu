@@ -91,8 +91,11 @@ __device__ __forceinline__ void mvt_produce(const ParamsMVT &p, uint32_t t, uint
     }
 }
 
-// UNIT: every operand has the eliminated variable at stride 1 (the canonical layout): immediate offsets
-template <int K, bool UNIT>
+// MODE 0: any stride of the eliminated variable.  MODE 1: every operand has it at stride 1 (the canonical layout):
+// immediate offsets.  MODE 2: stride 1, an even cardinality and every row on a 16-byte boundary: two values per
+// shared load (LDS.128) -- rows of an even number of doubles put the lanes of a warp on few banks, and the wider
+// load halves the wavefronts that costs.
+template <int K, int MODE>
 __global__ void __launch_bounds__(kBlock) contract_mvt(const __grid_constant__ ParamsMVT p)
 {
     extern __shared__ __align__(128) unsigned char mvt_smem[];
@@ -127,7 +130,20 @@ __global__ void __launch_bounds__(kBlock) contract_mvt(const __grid_constant__ P
 #pragma unroll
             for (int k = 0; k < K; ++k) row[k] = stage + p.soff[k] + (rowtab[j * K + k] + s_meta[s][k]);
             double acc = 0.0;
-            if (UNIT) {
+            if (MODE == 2) {
+#pragma unroll 2
+                for (uint32_t x = 0; x < cx; x += 2) {
+                    double2 a = *reinterpret_cast<const double2 *>(row[0] + x);
+#pragma unroll
+                    for (int k = 1; k < K; ++k) {
+                        const double2 b = *reinterpret_cast<const double2 *>(row[k] + x);
+                        a.x = __dmul_rn(a.x, b.x);
+                        a.y = __dmul_rn(a.y, b.y);
+                    }
+                    acc = __dadd_rn(acc, a.x);
+                    acc = __dadd_rn(acc, a.y);
+                }
+            } else if (MODE == 1) {
 #pragma unroll 4
                 for (uint32_t x = 0; x < cx; ++x) {
                     double a = row[0][x];
@@ -161,21 +177,27 @@ __global__ void __launch_bounds__(kBlock) contract_mvt(const __grid_constant__ P
 
 typedef void (*mvt_fn)(const ParamsMVT);
 
-mvt_fn pick_mvt(int k, bool unit)
+mvt_fn pick_mvt(int k, int mode)
 {
-    switch (k * 2 + (unit ? 1 : 0)) {
-    case 2: return contract_mvt<1, false>;
-    case 3: return contract_mvt<1, true>;
-    case 4: return contract_mvt<2, false>;
-    case 5: return contract_mvt<2, true>;
-    case 6: return contract_mvt<3, false>;
-    case 7: return contract_mvt<3, true>;
-    case 8: return contract_mvt<4, false>;
-    case 9: return contract_mvt<4, true>;
-    case 10: return contract_mvt<5, false>;
-    case 11: return contract_mvt<5, true>;
-    case 12: return contract_mvt<6, false>;
-    case 13: return contract_mvt<6, true>;
+    switch (k * 4 + mode) {
+    case 4: return contract_mvt<1, 0>;
+    case 5: return contract_mvt<1, 1>;
+    case 6: return contract_mvt<1, 2>;
+    case 8: return contract_mvt<2, 0>;
+    case 9: return contract_mvt<2, 1>;
+    case 10: return contract_mvt<2, 2>;
+    case 12: return contract_mvt<3, 0>;
+    case 13: return contract_mvt<3, 1>;
+    case 14: return contract_mvt<3, 2>;
+    case 16: return contract_mvt<4, 0>;
+    case 17: return contract_mvt<4, 1>;
+    case 18: return contract_mvt<4, 2>;
+    case 20: return contract_mvt<5, 0>;
+    case 21: return contract_mvt<5, 1>;
+    case 22: return contract_mvt<5, 2>;
+    case 24: return contract_mvt<6, 0>;
+    case 25: return contract_mvt<6, 1>;
+    case 26: return contract_mvt<6, 2>;
     default: return nullptr;
     }
 }
@@ -220,7 +242,7 @@ int plan_mvt(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *s
         if (split >= 0) top += (uint64_t)(g - 1) * axes[split].s[q];
         return top + 1;
     };
-    const uint64_t smem_budget = 100u << 10;        // two CTAs per SM
+    const uint64_t smem_budget = 110u << 10;        // two CTAs per SM
     const uint64_t e_max = 8192;
     // candidates: every suffix of axes as the inner block, every divisor g of the next axis; keep the best tile
     double best = -1.0;
@@ -351,7 +373,15 @@ int plan_mvt(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *s
             }
         }
     }
-    mvt_fn fn = pick_mvt(k, unit);
+    // two values per shared load: stride 1, even cardinality, and every row of every tile on a 16-byte boundary
+    bool pair = unit && cx % 2 == 0;
+    for (size_t i = 0; i < (size_t)T * k && pair; ++i) pair = tab[i] % 2 == 0;
+    for (int q = 0; q < k && pair; ++q) {
+        pair = p.s_split[q] % 2 == 0;
+        for (uint32_t a = 0; a < p.R && pair; ++a) pair = p.s[q][a] % 2 == 0;
+    }
+    const int mode = pair ? 2 : (unit ? 1 : 0);
+    mvt_fn fn = pick_mvt(k, mode);
     if (!fn) return 1;
     const unsigned smem = p.rowtab_bytes + stages * p.stage_doubles * 8u;
     const int per_sm = mvt_resident(ctx, fn, smem);
@@ -374,7 +404,7 @@ int plan_mvt(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *s
     d->fn = reinterpret_cast<const void *>(fn);
     d->grid = (unsigned)std::min<uint64_t>(p.n_tiles, (uint64_t)ctx->sm_count * per_sm);
     d->k = k;
-    d->variant = unit ? "mvt/unit" : "mvt/strided";
+    d->variant = mode == 2 ? "mvt/pair" : (mode == 1 ? "mvt/unit" : "mvt/strided");
     d->C = (int)cx;
     d->V = 1;
     d->U = (int)stages;

@@ -6,9 +6,15 @@
 // is the same schedule and the converging sweep index is preserved.
 // Messages live in two flat device arrays indexed by edge e = foff[f] + slot; the
 // host never touches them between sweeps except for the one max-error word.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 struct bnpp_fg {
     bnpp_ctx *ctx = nullptr;
@@ -32,6 +38,14 @@ struct bnpp_fg {
     double *marg = nullptr;
     uint32_t nmarg = 0;
     std::vector<uint32_t> h_card;
+    // FactorGraph::update as ONE cooperative launch: three rotating max-error words and the sweep count
+    unsigned long long *err3 = nullptr;         // device [3] + sweeps word [1]
+    uint32_t *sweeps_host = nullptr;            // pinned
+    int coop_blocks = 0;                        // 0 = not available (falls back to a launch per phase)
+    // factor -> variable updates: a thread per edge where the factor is small (fsize / card <= kSmallSub entries to sum
+    // per message entry: every Ising / pairwise factor), a warp per edge otherwise
+    int n_small = 0, n_big = 0;
+    int32_t *small_edges = nullptr, *big_edges = nullptr;
 };
 
 namespace bnpp {
@@ -56,6 +70,38 @@ __device__ __forceinline__ void note_error(unsigned long long *maxerr, double er
 }
 
 // variable -> factor, code/graph.cpp:334-362: m_{v->f} = normalize(prod_{g in N(v)\f} m_{g->v})
+__device__ __forceinline__ void var_to_fac_edge(int e, const uint32_t *__restrict__ evar, const uint32_t *__restrict__ card,
+                                                const uint32_t *__restrict__ moff, const int32_t *__restrict__ voff,
+                                                const int32_t *__restrict__ vedges, const double *f2v, double *v2f,
+                                                unsigned long long *maxerr)
+{
+    const uint32_t v = evar[e], r = card[v];
+    const int b = voff[v], n = voff[v + 1];
+    double z = 0.0;
+    for (uint32_t i = 0; i < r; ++i) {
+        double p = 1.0;
+        for (int q = b; q < n; ++q) {
+            const int e2 = vedges[q];
+            if (e2 != e) p *= __ldcg(f2v + moff[e2] + i);
+        }
+        z += p;
+    }
+    double worst = 0.0;
+    for (uint32_t i = 0; i < r; ++i) {
+        double p = 1.0;
+        for (int q = b; q < n; ++q) {
+            const int e2 = vedges[q];
+            if (e2 != e) p *= __ldcg(f2v + moff[e2] + i);
+        }
+        const double nv = p / z;
+        const double ov = __ldcg(v2f + moff[e] + i);
+        const double err = fabs(ov - nv) / ov;
+        if (err > worst) worst = err;
+        v2f[moff[e] + i] = nv;
+    }
+    note_error(maxerr, worst);
+}
+
 __global__ void __launch_bounds__(128) fg_var_to_fac_kernel(int nedges, const uint32_t *__restrict__ evar,
                                                             const uint32_t *__restrict__ card,
                                                             const uint32_t *__restrict__ moff,
@@ -66,50 +112,18 @@ __global__ void __launch_bounds__(128) fg_var_to_fac_kernel(int nedges, const ui
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nedges) return;
-    const uint32_t v = evar[e], r = card[v];
-    const int b = voff[v], n = voff[v + 1];
-    double z = 0.0;
-    for (uint32_t i = 0; i < r; ++i) {
-        double p = 1.0;
-        for (int q = b; q < n; ++q) {
-            const int e2 = vedges[q];
-            if (e2 != e) p *= f2v[moff[e2] + i];
-        }
-        z += p;
-    }
-    double worst = 0.0;
-    for (uint32_t i = 0; i < r; ++i) {
-        double p = 1.0;
-        for (int q = b; q < n; ++q) {
-            const int e2 = vedges[q];
-            if (e2 != e) p *= f2v[moff[e2] + i];
-        }
-        const double nv = p / z;
-        const double ov = v2f[moff[e] + i];
-        const double err = fabs(ov - nv) / ov;
-        if (err > worst) worst = err;
-        v2f[moff[e] + i] = nv;
-    }
-    note_error(maxerr, worst);
+    var_to_fac_edge(e, evar, card, moff, voff, vedges, f2v, v2f, maxerr);
 }
 
 // factor -> variable, code/graph.cpp:364-391: one warp per edge (f, slot j):
 // m_{f->v}[i] = sum over the factor entries with digit_j = i of  F * prod_{u != j} m_{u->f}
-__global__ void __launch_bounds__(128) fg_fac_to_var_kernel(int nedges, const int32_t *__restrict__ efac,
-                                                            const uint32_t *__restrict__ evar,
-                                                            const int32_t *__restrict__ foff,
-                                                            const uint32_t *__restrict__ card,
-                                                            const uint32_t *__restrict__ moff,
-                                                            const uint64_t *__restrict__ toff,
-                                                            const uint32_t *__restrict__ estride,
-                                                            const uint32_t *__restrict__ fsize,
-                                                            const double *__restrict__ ftab,
-                                                            const double *__restrict__ v2f, double *__restrict__ f2v,
-                                                            double *__restrict__ tmp, unsigned long long *maxerr)
+__device__ __forceinline__ void fac_to_var_edge(int e, int lane, const int32_t *__restrict__ efac,
+                                                const uint32_t *__restrict__ evar, const int32_t *__restrict__ foff,
+                                                const uint32_t *__restrict__ card, const uint32_t *__restrict__ moff,
+                                                const uint64_t *__restrict__ toff, const uint32_t *__restrict__ estride,
+                                                const uint32_t *__restrict__ fsize, const double *__restrict__ ftab,
+                                                const double *v2f, double *f2v, double *tmp, unsigned long long *maxerr)
 {
-    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (e >= nedges) return;
     const int f = efac[e];
     const int e0 = foff[f], w = foff[f + 1] - e0;
     const uint32_t r = card[evar[e]], stj = estride[e];
@@ -124,7 +138,7 @@ __global__ void __launch_bounds__(128) fg_fac_to_var_kernel(int nedges, const in
                 const int eu = e0 + u;
                 if (eu == e) continue;
                 const uint32_t d = (t / estride[eu]) % card[evar[eu]];
-                p *= v2f[moff[eu] + d];
+                p *= __ldcg(v2f + moff[eu] + d);
             }
             part += p;
         }
@@ -133,11 +147,11 @@ __global__ void __launch_bounds__(128) fg_fac_to_var_kernel(int nedges, const in
     }
     __syncwarp();
     double z = 0.0;
-    for (uint32_t i = 0; i < r; ++i) z += tmp[moff[e] + i];   // same order in every lane
+    for (uint32_t i = 0; i < r; ++i) z += __ldcg(tmp + moff[e] + i);   // same order in every lane
     double worst = 0.0;
     for (uint32_t i = lane; i < r; i += 32) {
-        const double nv = tmp[moff[e] + i] / z;
-        const double ov = f2v[moff[e] + i];
+        const double nv = __ldcg(tmp + moff[e] + i) / z;
+        const double ov = __ldcg(f2v + moff[e] + i);
         const double err = fabs(ov - nv) / ov;
         if (err > worst) worst = err;
         f2v[moff[e] + i] = nv;
@@ -148,6 +162,116 @@ __global__ void __launch_bounds__(128) fg_fac_to_var_kernel(int nedges, const in
         if (other > worst) worst = other;
     }
     if (lane == 0) note_error(maxerr, worst);
+}
+
+constexpr uint32_t kSmallSub = 8;
+
+// the same update by ONE thread (small factors: a warp per edge would leave 30 lanes idle)
+__device__ __forceinline__ void fac_to_var_edge_small(int e, const int32_t *__restrict__ efac, const uint32_t *__restrict__ evar,
+                                                      const int32_t *__restrict__ foff, const uint32_t *__restrict__ card,
+                                                      const uint32_t *__restrict__ moff, const uint64_t *__restrict__ toff,
+                                                      const uint32_t *__restrict__ estride, const uint32_t *__restrict__ fsize,
+                                                      const double *__restrict__ ftab, const double *v2f, double *f2v, double *tmp,
+                                                      unsigned long long *maxerr)
+{
+    const int f = efac[e];
+    const int e0 = foff[f], w = foff[f + 1] - e0;
+    const uint32_t r = card[evar[e]], stj = estride[e];
+    const uint32_t sub = fsize[f] / r;
+    const double *tab = ftab + toff[f];
+    double z = 0.0;
+    for (uint32_t i = 0; i < r; ++i) {
+        double part = 0.0;
+        for (uint32_t ts = 0; ts < sub; ++ts) {
+            const uint32_t t = (ts / stj) * (stj * r) + i * stj + (ts % stj);
+            double p = tab[t];
+            for (int u = 0; u < w; ++u) {
+                const int eu = e0 + u;
+                if (eu == e) continue;
+                const uint32_t d = (t / estride[eu]) % card[evar[eu]];
+                p *= __ldcg(v2f + moff[eu] + d);
+            }
+            part += p;
+        }
+        tmp[moff[e] + i] = part;
+        z += part;
+    }
+    double worst = 0.0;
+    for (uint32_t i = 0; i < r; ++i) {
+        const double nv = tmp[moff[e] + i] / z;
+        const double ov = __ldcg(f2v + moff[e] + i);
+        const double err = fabs(ov - nv) / ov;
+        if (err > worst) worst = err;
+        f2v[moff[e] + i] = nv;
+    }
+    note_error(maxerr, worst);
+}
+
+__global__ void __launch_bounds__(128) fg_fac_to_var_kernel(int n_small, const int32_t *__restrict__ small_edges, int n_big,
+                                                            const int32_t *__restrict__ big_edges,
+                                                            const int32_t *__restrict__ efac,
+                                                            const uint32_t *__restrict__ evar,
+                                                            const int32_t *__restrict__ foff,
+                                                            const uint32_t *__restrict__ card,
+                                                            const uint32_t *__restrict__ moff,
+                                                            const uint64_t *__restrict__ toff,
+                                                            const uint32_t *__restrict__ estride,
+                                                            const uint32_t *__restrict__ fsize,
+                                                            const double *__restrict__ ftab,
+                                                            const double *__restrict__ v2f, double *__restrict__ f2v,
+                                                            double *__restrict__ tmp, unsigned long long *maxerr)
+{
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    for (int i = gtid; i < n_small; i += gthreads)
+        fac_to_var_edge_small(small_edges[i], efac, evar, foff, card, moff, toff, estride, fsize, ftab, v2f, f2v, tmp, maxerr);
+    const int lane = threadIdx.x & 31;
+    for (int i = gtid >> 5; i < n_big; i += gthreads >> 5)
+        fac_to_var_edge(big_edges[i], lane, efac, evar, foff, card, moff, toff, estride, fsize, ftab, v2f, f2v, tmp, maxerr);
+}
+
+// FactorGraph::update (code/graph.cpp:298-332) as ONE cooperative launch: every sweep is the two floods above with a
+// grid-wide barrier after each; the convergence test `maxerror < epsilon` and the sweep counter stay on the device, the
+// host reads (sweeps) once.  A 40x40 Ising sweep is 15 680 two-entry messages: launch latency, not work, is what a
+// launch per phase pays.  The max-error word rotates over three slots so that zeroing the next sweep's slot never
+// races with a slow block still reading the previous one.
+struct FgArgs {
+    int nedges;
+    const uint32_t *evar, *card, *moff;
+    const int32_t *voff, *vedges, *efac, *foff;
+    const uint64_t *toff;
+    const uint32_t *estride, *fsize;
+    const double *ftab;
+    double *f2v, *v2f, *tmp;
+    int n_small, n_big;
+    const int32_t *small_edges, *big_edges;
+    unsigned long long *err3;      // [3] max-error slots, [3] = sweeps (as uint32)
+    uint32_t max_sweeps;
+    double epsilon;
+};
+
+__global__ void __launch_bounds__(256) fg_update_kernel(const FgArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    const int gwarp = gtid >> 5, gwarps = gthreads >> 5, lane = threadIdx.x & 31;
+    uint32_t it = 0;
+    for (; it < a.max_sweeps; ++it) {
+        unsigned long long *err = a.err3 + it % 3;
+        if (gtid == 0) a.err3[(it + 1) % 3] = 0ull;
+        for (int e = gtid; e < a.nedges; e += gthreads)
+            var_to_fac_edge(e, a.evar, a.card, a.moff, a.voff, a.vedges, a.f2v, a.v2f, err);
+        grid.sync();
+        for (int i = gtid; i < a.n_small; i += gthreads)
+            fac_to_var_edge_small(a.small_edges[i], a.efac, a.evar, a.foff, a.card, a.moff, a.toff, a.estride, a.fsize, a.ftab,
+                                  a.v2f, a.f2v, a.tmp, err);
+        for (int i = gwarp; i < a.n_big; i += gwarps)
+            fac_to_var_edge(a.big_edges[i], lane, a.efac, a.evar, a.foff, a.card, a.moff, a.toff, a.estride, a.fsize, a.ftab,
+                            a.v2f, a.f2v, a.tmp, err);
+        grid.sync();
+        const double maxerror = __longlong_as_double((long long)*reinterpret_cast<volatile unsigned long long *>(err));
+        if (maxerror < a.epsilon) break;          // code/graph.cpp:328, the same decision in every thread
+    }
+    if (gtid == 0) *reinterpret_cast<uint32_t *>(a.err3 + 3) = it;
 }
 
 // FactorGraph::marginal, code/graph.cpp:393-403
@@ -226,6 +350,9 @@ int bnpp_fg_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfac, con
     }
     std::vector<uint32_t> mvoff(nvars + 1, 0);
     for (int v = 0; v < nvars; ++v) mvoff[v + 1] = mvoff[v] + card[v];
+    std::vector<int32_t> small_edges, big_edges;
+    for (int e = 0; e < nedges; ++e)
+        (fsize[efac[e]] / card[evar[e]] <= kSmallSub ? small_edges : big_edges).push_back(e);
 
     bnpp_fg *g = new bnpp_fg();
     g->ctx = ctx;
@@ -238,7 +365,9 @@ int bnpp_fg_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfac, con
     int rc;
 #define UP(field, vec) if ((rc = to_device(ctx, &g->field, vec)) != BNPP_OK) { bnpp_fg_destroy(g); return rc; }
     UP(card, h_card) UP(foff, h_foff) UP(evar, evar) UP(efac, efac) UP(moff, moff) UP(voff, voff) UP(vedges, vedges)
-    UP(toff, h_toff) UP(estride, estride) UP(fsize, fsize) UP(mvoff, mvoff)
+    UP(toff, h_toff) UP(estride, estride) UP(fsize, fsize) UP(mvoff, mvoff) UP(small_edges, small_edges) UP(big_edges, big_edges)
+    g->n_small = (int)small_edges.size();
+    g->n_big = (int)big_edges.size();
 #undef UP
     BNPP_CUDA(ctx, cudaMalloc(&g->ftab, sizeof(double) * (tab_total ? tab_total : 1)));
     if (tab_total)
@@ -250,6 +379,23 @@ int bnpp_fg_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfac, con
     BNPP_CUDA(ctx, cudaMalloc(&g->marg, sizeof(double) * (g->nmarg ? g->nmarg : 1)));
     BNPP_CUDA(ctx, cudaMalloc(&g->maxerr, sizeof(unsigned long long)));
     BNPP_CUDA(ctx, cudaMallocHost(&g->maxerr_host, sizeof(unsigned long long)));
+    BNPP_CUDA(ctx, cudaMalloc(&g->err3, 4 * sizeof(unsigned long long)));
+    BNPP_CUDA(ctx, cudaMallocHost(&g->sweeps_host, sizeof(uint32_t)));
+    {
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fg_update_kernel, 256, 0) == cudaSuccess && per_sm > 0) {
+            // enough warps for one edge each where possible, never more than fits at once (a grid barrier needs all
+            // blocks resident); fewer blocks make the barrier cheaper
+            int want = (int)((small_edges.size() + 32 * big_edges.size() + 255) / 256);
+            if (const char *env = getenv("BNPP_FG_BLOCKS")) want = atoi(env);
+            const int cap = ctx->sm_count * (per_sm < 2 ? per_sm : 2);
+            if (want > cap) want = cap;
+            if (want < 1) want = 1;
+            g->coop_blocks = want;
+        }
+        cudaGetLastError();
+    }
     if (nedges) {
         fg_init_kernel<<<(nedges + 127) / 128, 128, 0, ctx->stream>>>(nedges, g->evar, g->card, g->moff, g->f2v, g->v2f);
         BNPP_CUDA(ctx, cudaGetLastError());
@@ -267,8 +413,9 @@ int bnpp_fg_destroy(bnpp_fg *g)
     cudaFree(g->card); cudaFree(g->foff); cudaFree(g->evar); cudaFree(g->efac); cudaFree(g->moff);
     cudaFree(g->voff); cudaFree(g->vedges); cudaFree(g->toff); cudaFree(g->estride); cudaFree(g->fsize);
     cudaFree(g->mvoff); cudaFree(g->ftab); cudaFree(g->f2v); cudaFree(g->v2f); cudaFree(g->tmp);
-    cudaFree(g->marg); cudaFree(g->maxerr);
+    cudaFree(g->marg); cudaFree(g->maxerr); cudaFree(g->err3); cudaFree(g->small_edges); cudaFree(g->big_edges);
     if (g->maxerr_host) cudaFreeHost(g->maxerr_host);
+    if (g->sweeps_host) cudaFreeHost(g->sweeps_host);
     delete g;
     return BNPP_OK;
 }
@@ -281,8 +428,8 @@ static int fg_launch_sweep(bnpp_fg *g)
         fg_var_to_fac_kernel<<<(g->nedges + 127) / 128, 128, 0, ctx->stream>>>(
             g->nedges, g->evar, g->card, g->moff, g->voff, g->vedges, g->f2v, g->v2f, g->maxerr);
         BNPP_CUDA(ctx, cudaGetLastError());
-        fg_fac_to_var_kernel<<<(g->nedges * 32 + 127) / 128, 128, 0, ctx->stream>>>(
-            g->nedges, g->efac, g->evar, g->foff, g->card, g->moff, g->toff, g->estride, g->fsize, g->ftab, g->v2f,
+        fg_fac_to_var_kernel<<<(g->n_small + 32 * g->n_big + 127) / 128, 128, 0, ctx->stream>>>(
+            g->n_small, g->small_edges, g->n_big, g->big_edges, g->efac, g->evar, g->foff, g->card, g->moff, g->toff, g->estride, g->fsize, g->ftab, g->v2f,
             g->f2v, g->tmp, g->maxerr);
         BNPP_CUDA(ctx, cudaGetLastError());
         ctx->launches += 2;
@@ -308,6 +455,31 @@ int bnpp_fg_sweep(bnpp_fg *g, double *maxerror_host)
 int bnpp_fg_update(bnpp_fg *g, uint32_t max_sweeps, double epsilon, uint32_t *sweeps)
 {
     if (!g) return BNPP_EINVAL;
+    bnpp_ctx *ctx = g->ctx;
+    if (g->coop_blocks > 0 && g->nedges > 0 && max_sweeps > 0) {
+        // the whole loop in one cooperative launch; the host reads the sweep count once
+        FgArgs a;
+        a.nedges = g->nedges;
+        a.evar = g->evar; a.card = g->card; a.moff = g->moff; a.voff = g->voff; a.vedges = g->vedges;
+        a.efac = g->efac; a.foff = g->foff; a.toff = g->toff; a.estride = g->estride; a.fsize = g->fsize;
+        a.ftab = g->ftab; a.f2v = g->f2v; a.v2f = g->v2f; a.tmp = g->tmp; a.err3 = g->err3;
+        a.n_small = g->n_small; a.n_big = g->n_big; a.small_edges = g->small_edges; a.big_edges = g->big_edges;
+        a.max_sweeps = max_sweeps;
+        a.epsilon = epsilon;
+        BNPP_CUDA(ctx, cudaMemsetAsync(g->err3, 0, 4 * sizeof(unsigned long long), ctx->stream));
+        void *args[1] = {&a};
+        cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(fg_update_kernel), dim3(g->coop_blocks), dim3(256),
+                                                    args, 0, ctx->stream);
+        if (e == cudaSuccess) {
+            ctx->launches++;
+            BNPP_CUDA(ctx, cudaMemcpyAsync(g->sweeps_host, g->err3 + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            BNPP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (sweeps) *sweeps = *g->sweeps_host;
+            return BNPP_OK;
+        }
+        cudaGetLastError();
+        g->coop_blocks = 0;         // not launchable here (e.g. under a capture): a launch per phase from now on
+    }
     uint32_t it;
     for (it = 0; it < max_sweeps; ++it) {
         double maxerror = 0.0;
@@ -316,6 +488,19 @@ int bnpp_fg_update(bnpp_fg *g, uint32_t max_sweeps, double epsilon, uint32_t *sw
         if (maxerror < epsilon) break;   // code/graph.cpp:328
     }
     if (sweeps) *sweeps = it;
+    return BNPP_OK;
+}
+
+// messages back to the uniform start of code/graph.cpp:261-274 (a second update() on the same graph)
+int bnpp_fg_reset(bnpp_fg *g)
+{
+    if (!g) return BNPP_EINVAL;
+    bnpp_ctx *ctx = g->ctx;
+    if (g->nedges) {
+        fg_init_kernel<<<(g->nedges + 127) / 128, 128, 0, ctx->stream>>>(g->nedges, g->evar, g->card, g->moff, g->f2v, g->v2f);
+        BNPP_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
     return BNPP_OK;
 }
 

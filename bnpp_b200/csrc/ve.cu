@@ -99,6 +99,11 @@ struct bnpp_ve_plan {
     bnpp_ctx *ctx = nullptr;
     int n_inputs = 0;
     int n_obs = 0;
+    std::vector<uint32_t> obs_card;         // cardinality per observed variable (0 = no factor mentions it)
+    uint32_t *obs_card_dev = nullptr;       // device copy, made by the first batched run
+    uint8_t *ev_clean = nullptr;            // batched fused runs: the evidence matrix with out-of-range values zeroed
+    uint64_t ev_clean_bytes = 0;
+    bool normalize = true;                  // marginals plan: normalise the slices at the end of a run
     int fused_mode = 1;                     // 0: one launch per bucket always; 1: one launch per plan when every step is small
     bnpp::FusedProgram fused;
     // EXPERIMENTAL (off unless BNPP_FUSED_SEGMENTS=1 or bnpp_ve_plan_set_segments): inside a launch-per-bucket plan,
@@ -296,6 +301,7 @@ int add_inputs(bnpp_ve_plan *pl, int nfac, const bnpp_scope *scopes, const std::
             auto o = obs_index.find(s.var_id[i]);
             if (o != obs_index.end()) {
                 pf.obs.push_back({st[i], o->second});
+                if ((size_t)o->second < pl->obs_card.size()) pl->obs_card[o->second] = s.card[i];
                 continue;
             }
             pf.var.push_back(s.var_id[i]);
@@ -917,6 +923,7 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
     pl->ctx = ctx;
     pl->n_inputs = nfac;
     pl->n_obs = n_obs;
+    pl->obs_card.assign(n_obs, 0);
     pl->fused_mode = fused_default_on() ? 1 : 0;
     pl->segments_mode = segments_default_on() ? 1 : 0;
 
@@ -1000,6 +1007,7 @@ int bnpp_mar_plan_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfa
     pl->ctx = ctx;
     pl->n_inputs = nfac;
     pl->n_obs = n_obs;
+    pl->obs_card.assign(n_obs, 0);
     pl->fused_mode = fused_default_on() ? 1 : 0;
     pl->segments_mode = segments_default_on() ? 1 : 0;
     pl->is_mar = true;
@@ -1150,6 +1158,8 @@ int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
     if (pl->fused.prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.prog_dev));
     if (pl->fused.offtab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.offtab_dev));
     if (pl->mar_off_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->mar_off_dev));
+    if (pl->obs_card_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->obs_card_dev));
+    if (pl->ev_clean) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->ev_clean));
     for (uint32_t *t : pl->offtab_dev)
         if (t) bnpp_free(pl->ctx, reinterpret_cast<double *>(t));
     delete pl;
@@ -1172,6 +1182,26 @@ int bnpp_ve_plan_info(const bnpp_ve_plan *pl, int32_t *result_rank, uint32_t *re
     if (peak_bytes) *peak_bytes = pl->peak_bytes;
     if (max_step_entries) *max_step_entries = pl->max_step_entries;
     return BNPP_OK;
+}
+
+int bnpp_ve_plan_result_size(const bnpp_ve_plan *pl, uint64_t *n)
+{
+    if (!pl || !n) return BNPP_EINVAL;
+    *n = pl->result_size;
+    return BNPP_OK;
+}
+
+int bnpp_ve_plan_set_normalize(bnpp_ve_plan *pl, int on)
+{
+    if (!pl) return BNPP_EINVAL;
+    pl->normalize = on != 0;
+    return BNPP_OK;
+}
+
+int bnpp_mar_plan_normalize(bnpp_ve_plan *pl, double *result_dev)
+{
+    if (!pl || !pl->ctx || !pl->is_mar || !result_dev) return BNPP_EINVAL;
+    return normalize_segments(pl->ctx, result_dev, pl->mar_off_dev, pl->mar_size_dev, (int)pl->mar_off.size());
 }
 
 int bnpp_ve_plan_set_profiling(bnpp_ve_plan *pl, int on)
@@ -1426,6 +1456,10 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
 {
     if (!pl || !pl->ctx || !result_dev) return BNPP_EINVAL;
     bnpp_ctx *ctx = pl->ctx;
+    if (pl->n_obs && !obs_val) return fail(ctx, BNPP_EINVAL, "VE plan: evidence values missing");
+    for (int i = 0; i < pl->n_obs; ++i)
+        if (pl->obs_card[i] && obs_val[i] >= pl->obs_card[i])
+            return fail(ctx, BNPP_EINVAL, "VE plan: evidence value out of range (Factor::operator[], code/factor.cpp:83-95)");
     std::vector<const double *> ptr(pl->f.size(), nullptr);
     bool aligned32 = true;
     for (size_t i = 0; i < pl->f.size(); ++i) {
@@ -1525,7 +1559,7 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             for (size_t s = 0; s < pl->steps.size(); ++s) pl->step_kernel[s] = pl->exec[s].name();
         }
     }
-    if (rc == BNPP_OK && pl->is_mar)
+    if (rc == BNPP_OK && pl->is_mar && pl->normalize)
         rc = normalize_segments(ctx, result_dev, pl->mar_off_dev, pl->mar_size_dev, (int)pl->mar_off.size());
     if (pl->profiling) cudaEventRecord(pl->ev[pl->steps.size()], ctx->stream);
     pl->runs++;
@@ -1547,10 +1581,40 @@ int bnpp_ve_plan_run_batched(bnpp_ve_plan *pl, const double *const *tables_dev, 
 {
     if (!pl || !pl->ctx || !result_dev || nb == 0) return BNPP_EINVAL;
     bnpp_ctx *ctx = pl->ctx;
-    if ((int)n_obs == pl->n_obs && (ev_dev || n_obs == 0) && nb > 1) {
+    if ((int)n_obs != pl->n_obs) return fail(ctx, BNPP_EINVAL, "batched VE: n_obs differs from the plan's");
+    if (n_obs && !ev_dev) return fail(ctx, BNPP_EINVAL, "batched VE: evidence matrix missing");
+    if (n_obs && !pl->obs_card_dev) {
+        double *store = nullptr;
+        const int rc = bnpp_alloc(ctx, n_obs / 2 + 2, &store);
+        if (rc != BNPP_OK) return rc;
+        pl->obs_card_dev = reinterpret_cast<uint32_t *>(store);
+        std::vector<uint32_t> c(pl->obs_card);
+        for (uint32_t &v : c)
+            if (!v) v = 256;        // a variable no factor mentions: any byte is harmless
+        BNPP_CUDA(ctx, cudaMemcpyAsync(pl->obs_card_dev, c.data(), sizeof(uint32_t) * n_obs, cudaMemcpyHostToDevice, ctx->stream));
+        BNPP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));       // `c` dies here
+    }
+    if (nb > 1) {
         // K9: one launch for the whole batch, the intermediates of a set never leave shared memory
         const int G = fused_pick(pl, nb);
-        if (G) return run_fused(pl, G, tables_dev, nb, ev_dev, nullptr, result_dev, nullptr);
+        if (G) {
+            const uint8_t *ev = ev_dev;
+            if (n_obs) {
+                const uint64_t need = (uint64_t)nb * n_obs;
+                if (pl->ev_clean_bytes < need) {
+                    if (pl->ev_clean) bnpp_free(ctx, reinterpret_cast<double *>(pl->ev_clean));
+                    double *store = nullptr;
+                    const int rc = bnpp_alloc(ctx, need / 8 + 2, &store);
+                    if (rc != BNPP_OK) return rc;
+                    pl->ev_clean = reinterpret_cast<uint8_t *>(store);
+                    pl->ev_clean_bytes = need;
+                }
+                const int rc = sanitize_evidence_launch(ctx, ev_dev, pl->ev_clean, nb, n_obs, pl->obs_card_dev, false);
+                if (rc != BNPP_OK) return rc;
+                ev = pl->ev_clean;
+            }
+            return run_fused(pl, G, tables_dev, nb, ev, nullptr, result_dev, nullptr);
+        }
     }
     std::vector<const void *> key;
     key.push_back(ev_dev);
@@ -1616,7 +1680,7 @@ static int run_batched_once(bnpp_ve_plan *pl, const double *const *tables_dev, u
         pl->offtab_host.assign(pl->steps.size(), std::vector<uint32_t>());
         pl->offtab_dev.assign(pl->steps.size(), nullptr);
     }
-    rc = transpose_evidence_launch(ctx, ev_dev, evt, nb, n_obs);
+    rc = sanitize_evidence_launch(ctx, ev_dev, evt, nb, n_obs, pl->obs_card_dev, true);
     for (uint32_t b0 = 0; b0 < nb && rc == BNPP_OK; b0 += slice) {
         const uint32_t cur = std::min(slice, nb - b0);
         std::vector<double *> owned(pl->f.size(), nullptr);

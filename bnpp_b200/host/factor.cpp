@@ -133,6 +133,9 @@ const double *Factor::device_data() const
 {
     if (!_dev_valid) {
         const uint64_t n = size();
+        // a table with fewer values than its scope implies (a malformed UAI file): the reference dies in
+        // _values.at(); uploading n doubles from a shorter vector would read past the heap buffer
+        if (_host.size() < n) throw "Factor: table holds fewer values than its domain.";
         if (!_dev) _dev = device_alloc(n + 1);
         gpu::check(bnpp_upload(gpu::ctx(), _dev, _host.data(), n), "bnpp_upload");
         gpu::check(bnpp_fill(gpu::ctx(), dev_z(), 1, _partition), "bnpp_fill");

@@ -21,13 +21,15 @@ bool next_token(std::ifstream &in, std::string &tok)
 unsigned next_unsigned(std::ifstream &in)
 {
     std::string tok;
-    return next_token(in, tok) ? (unsigned)std::stoi(tok) : 0u;
+    next_token(in, tok);
+    return (unsigned)std::stoi(tok);      // at end of file tok is empty and stoi throws, as in the reference (code/io.cpp:25-33)
 }
 
 double next_double(std::ifstream &in)
 {
     std::string tok;
-    return next_token(in, tok) ? std::stod(tok) : 0.0;
+    next_token(in, tok);
+    return std::stod(tok);                // a truncated table is an error, not zeros
 }
 
 // Well-formed files: one read, tokens scanned in place (uai_parse.hpp).  false = "not sure": the caller

@@ -36,6 +36,9 @@ def _declare(L):
                                        capi.c_u32p, ctypes.c_int, capi.c_u32p, P(ctypes.c_void_p)]
     L.bnpp_mar_plan_layout.argtypes = [ctypes.c_void_p, ctypes.c_int, capi.c_u32p, capi.c_u32p, capi.c_u64p]
     L.bnpp_ve_plan_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.bnpp_ve_plan_set_normalize.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.bnpp_mar_plan_normalize.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.bnpp_ve_plan_result_size.argtypes = [ctypes.c_void_p, capi.c_u64p]
     L.bnpp_ve_plan_set_fused.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.bnpp_ve_plan_fused_info.argtypes = [ctypes.c_void_p, ctypes.c_uint32, P(ctypes.c_int32), capi.c_u32p, capi.c_u32p]
     L.bnpp_ve_plan_set_segments.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32]
@@ -233,6 +236,8 @@ class BN:
             self._dev.copy_(self._host, non_blocking=True)
         self.table_ptrs = [self._dev.data_ptr() + 8 * o for o in offs]
         self._plans = {}
+        self._shard_cache = {}
+        self._batch_plans = {}
         self._res2 = None
         self._batch_out = {}
         self.last_timing = {}
@@ -275,10 +280,38 @@ class BN:
         p.run(self.table_ptrs, [evidence[v] for v in observed], res.data_ptr(), res.data_ptr() + 8 * p.result_size)
         return p.result_scope, p.result_cards, res
 
-    def partition(self, evidence=None, heuristic=None):
-        """BN::partition, VE branch (code/model.cpp:275-294) -> (Z, uptime_ms)"""
+    def shard(self, evidence, heuristic, comm):
+        """wide-factor sharding: the log2(world) variables of the widest elimination clique that the order
+        of the UNSHARDED query eliminates last, observed at this rank's values -> (evidence incl. shard values, shard vars)"""
+        from . import sharding
+        g = (comm.world - 1).bit_length() if comm is not None else 0
+        if g == 0:
+            return dict(evidence), []
+        if (1 << g) != comm.world:
+            raise ValueError("wide-factor sharding needs a power-of-two number of ranks")
+        key = (tuple(sorted(evidence)), heuristic, g)
+        shard_vars = self._shard_cache.get(key)
+        if shard_vars is None:
+            variables = [v for v in range(self.nvars) if v not in evidence]
+            full_order, _ = self.order(variables, evidence, heuristic)
+            live = self.conditioned_scopes(set(evidence))
+            shard_vars = [v for v in sharding.pick_shard_vars(live, full_order, g)]
+            if len(shard_vars) != g or any(self.cards[v] != 2 for v in shard_vars):
+                raise ValueError("no %d binary shard variables in the widest clique" % g)
+            self._shard_cache[key] = shard_vars
+        full = dict(evidence)
+        full.update(sharding.shard_evidence(shard_vars, comm.rank))
+        return full, shard_vars
+
+    def partition(self, evidence=None, heuristic=None, comm=None):
+        """BN::partition, VE branch (code/model.cpp:275-294) -> (Z, uptime_ms).
+        comm (a nccl.ShardComm over all ranks): the network is sharded over the ranks by the leading variables of its
+        widest clique, every rank eliminates its slab and the partition is summed over NVLink (bnpp_ve_plan_run_sharded);
+        every rank returns the same Z."""
         t0 = time.perf_counter()
         evidence = dict(evidence or {})
+        if comm is not None and comm.world > 1:
+            evidence, _ = self.shard(evidence, heuristic, comm)
         variables = [v for v in range(self.nvars) if v not in evidence]
         order, _ = self.order(variables, evidence, heuristic)
         t1 = time.perf_counter()
@@ -290,13 +323,16 @@ class BN:
                 self._res2 = torch.empty(2, dtype=torch.float64, device=self._dev.device)
                 self._res2_host = torch.empty(2, dtype=torch.float64).pin_memory()
         assert p.result_size == 1
-        p.run(self.table_ptrs, [evidence[v] for v in observed], self._res2.data_ptr(), self._res2.data_ptr() + 8)
+        if comm is not None and comm.world > 1:
+            comm.run_sharded(p, self.table_ptrs, [evidence[v] for v in observed], self._res2.data_ptr(), self._res2.data_ptr() + 8)
+        else:
+            p.run(self.table_ptrs, [evidence[v] for v in observed], self._res2.data_ptr(), self._res2.data_ptr() + 8)
         with torch.cuda.stream(self.ctx.torch_stream):
             self._res2_host.copy_(self._res2, non_blocking=True)
         self.ctx.sync()
         t3 = time.perf_counter()
         z0, z1 = self._res2_host.tolist()
-        assert z0 == z1      # code/model.cpp:288
+        assert z0 == z1 or (comm is not None and abs(z0 - z1) <= 1e-12 * abs(z1))     # code/model.cpp:288
         self.last_timing = {"order_ms": (t1 - t0) * 1e3, "plan_ms": (t2 - t1) * 1e3, "run_ms": (t3 - t2) * 1e3}
         return z1, (time.perf_counter() - t0) * 1e3
 
@@ -305,9 +341,14 @@ class BN:
         observed: sorted variable ids; values: torch.uint8 CUDA tensor [nb][len(observed)] (or pass
         host_values, a pinned uint8 tensor, to include the H2D copy).  -> device tensor [nb] of Z."""
         observed = list(observed)
-        variables = [v for v in range(self.nvars) if v not in set(observed)]
-        order, _ = self.order(variables, observed, heuristic)
-        p = self.plan(observed, order)
+        # one plan per (observed ids, heuristic): the order depends on the ids only, so repeated batches over the same
+        # ids pay neither the host ordering nor the planning again (drop_plans() forgets it)
+        bkey = (tuple(observed), heuristic)
+        p = self._batch_plans.get(bkey)
+        if p is None:
+            variables = [v for v in range(self.nvars) if v not in set(observed)]
+            order, _ = self.order(variables, observed, heuristic)
+            p = self._batch_plans[bkey] = self.plan(observed, order)
         assert p.result_size == 1
         with torch.cuda.stream(self.ctx.torch_stream):
             if host_values is not None:
@@ -321,10 +362,14 @@ class BN:
         self._keep_alive = values
         return out
 
-    def marginals_fast(self, evidence=None, heuristic="mf"):
+    def marginals_fast(self, evidence=None, heuristic="mf", comm=None):
         """every marginal from ONE bucket-tree plan (two passes) instead of one VE pass per variable;
-        same tables as `marginals` up to rounding.  -> list of arrays ([1.0] for observed variables)"""
+        same tables as `marginals` up to rounding.  -> list of arrays ([1.0] for observed variables).
+        comm: the network sharded over the ranks (see `partition`): unnormalised slices P(v, e, shard = rank's values)
+        are summed over NVLink, then normalised; the shard variables' own marginals come from the ranks' partitions."""
         evidence = dict(evidence or {})
+        if comm is not None and comm.world > 1:
+            return self._marginals_sharded(evidence, heuristic, comm)
         observed = sorted(evidence)
         variables = [v for v in range(self.nvars) if v not in evidence]
         order, _ = self.order(variables, evidence, heuristic)
@@ -339,6 +384,48 @@ class BN:
         self.ctx.sync()
         host = res.cpu().numpy()
         return [host[o:o + n] for o, n in zip(p.off, p.size)]
+
+    def _marginals_sharded(self, evidence, heuristic, comm):
+        from . import sharding
+        full, shard_vars = self.shard(evidence, heuristic, comm)
+        observed = sorted(full)
+        variables = [v for v in range(self.nvars) if v not in full]
+        order, _ = self.order(variables, full, heuristic)
+        key = ("mar", tuple(observed), tuple(order))
+        p = self._plans.get(key)
+        if p is None:
+            p = MarPlan(self.ctx, self.cards, self.scopes, observed, order, _arr=self._scope_arr)
+            self._plans[key] = p
+        L = self.ctx.L
+        n = max(1, p.result_size)
+        with torch.cuda.stream(self.ctx.torch_stream):
+            res = torch.zeros(n + comm.world, dtype=torch.float64, device=self._dev.device)
+        self.ctx.check(L.bnpp_ve_plan_set_normalize(p.h, 0))
+        try:
+            p.run(self.table_ptrs, [full[v] for v in observed], res.data_ptr(), None)
+        finally:
+            self.ctx.check(L.bnpp_ve_plan_set_normalize(p.h, 1))
+        # this rank's partition = the sum of any unobserved variable's unnormalised slice
+        probe = next((v for v in variables if p.size[v] == self.cards[v]), None)
+        with torch.cuda.stream(self.ctx.torch_stream):
+            if probe is None:
+                z, _ = self.partition(full, heuristic)
+                res[n + comm.rank] = z
+            else:
+                res[n + comm.rank] = res[p.off[probe]:p.off[probe] + p.size[probe]].sum()
+        comm.allreduce_sum(res.data_ptr(), n + comm.world)          # the cross-shard sum-out (slices) + every rank's Z
+        L.bnpp_mar_plan_normalize.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+        self.ctx.check(L.bnpp_mar_plan_normalize(p.h, ctypes.c_void_p(res.data_ptr())))
+        self.ctx.sync()
+        host = res.cpu().numpy()
+        out = [host[o:o + s_].copy() for o, s_ in zip(p.off, p.size)]
+        zr = host[n:n + comm.world]
+        for v in shard_vars:
+            m = np.zeros(self.cards[v])
+            for r in range(comm.world):
+                m[sharding.shard_evidence(shard_vars, r)[v]] += zr[r]
+            out[v] = m / zr.sum()
+        return out
 
     def marginals(self, evidence=None, heuristic=None):
         """BN::marginals, VE branch (code/model.cpp:320-339): one VE pass per variable, normalised.
@@ -371,6 +458,7 @@ class BN:
         for p in self._plans.values():
             p.close()
         self._plans = {}
+        self._batch_plans = {}
 
     def close(self):
         self.drop_plans()

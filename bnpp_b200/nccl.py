@@ -20,6 +20,7 @@ class ShardComm:
     def __init__(self, ctx, rank=0, world=1):
         import torch.distributed as dist
         self.ctx = ctx
+        self.rank, self.world = rank, world
         self.nccl = ctypes.CDLL("libnccl.so.2")
         self.lib = ctypes.CDLL(os.path.join(_HERE, "libbnpp_b200_nccl.so"))
         self.lib.bnpp_shard_allreduce_sum.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
@@ -36,6 +37,16 @@ class ShardComm:
         self.nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _UniqueId, ctypes.c_int]
         rc = self.nccl.ncclCommInitRank(ctypes.byref(self.comm), world, uid, rank)
         assert rc == 0, "ncclCommInitRank failed (%d)" % rc
+
+    def run_sharded(self, plan, table_ptrs, obs_val, result_ptr, z_ptr=None):
+        """bnpp_ve_plan_run_sharded: this rank's slab of the plan, then the cross-shard sum-out of result and partition"""
+        n = len(table_ptrs)
+        tp = (ctypes.c_void_p * max(1, n))(*table_ptrs)
+        ov = capi._u32(obs_val)
+        self.lib.bnpp_ve_plan_run_sharded.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p),
+                                                      capi.c_u32p, ctypes.c_void_p, ctypes.c_void_p]
+        self.ctx.check(self.lib.bnpp_ve_plan_run_sharded(self.ctx.h, plan.h, self.comm, tp, ctypes.cast(ov, capi.c_u32p),
+                                                         ctypes.c_void_p(result_ptr), ctypes.c_void_p(z_ptr) if z_ptr else None))
 
     def allreduce_sum(self, ptr, n):
         """in place, on the context's stream"""

@@ -54,6 +54,11 @@ class FactorGraph:
         self.ctx.check(self.ctx.L.bnpp_fg_update(self.h, max_sweeps, epsilon, ctypes.byref(n)))
         return n.value
 
+    def reset(self):
+        """messages back to the uniform start, code/graph.cpp:261-274"""
+        self.ctx.L.bnpp_fg_reset.argtypes = [ctypes.c_void_p]
+        self.ctx.check(self.ctx.L.bnpp_fg_reset(self.h))
+
     def marginals(self):
         """FactorGraph::marginal for every variable, code/graph.cpp:393-403 -> list of arrays"""
         out = np.zeros(int(self.cards.sum()))

@@ -44,6 +44,7 @@ extern "C" {
 
 /* status bits accumulated on the device, read with bnpp_ctx_status */
 #define BNPP_STATUS_ZERO_DIVISOR 1u   /* code/factor.cpp:169 asserts on this */
+#define BNPP_STATUS_BAD_EVIDENCE 2u   /* a batched evidence value >= its variable's cardinality (replaced by 0); code/factor.cpp:83-95 throws */
 
 typedef struct bnpp_ctx bnpp_ctx;
 
@@ -184,9 +185,13 @@ int bnpp_ve_plan_info(const bnpp_ve_plan *plan, int32_t *result_rank, uint32_t *
                       uint64_t *n_launches, uint64_t *union_entries, uint64_t *algorithmic_bytes,
                       uint64_t *peak_bytes, uint64_t *max_step_entries);
 /* tables_dev[nfac]: device tables; obs_val[n_obs]: evidence values; result_dev: device
- * buffer of the result's size; z_dev: optional device double for its partition.  Asynchronous. */
+ * buffer of the result's size; z_dev: optional device double for its partition.  Asynchronous.
+ * An evidence value >= its variable's cardinality returns BNPP_EINVAL (the reference throws from
+ * Factor::operator[], code/factor.cpp:83-95). */
 int bnpp_ve_plan_run(bnpp_ve_plan *plan, const double *const *tables_dev, const uint32_t *obs_val,
                      double *result_dev, double *z_dev);
+/* entries of the result table a run writes (PR: 1; marginals plan: the layout's total) */
+int bnpp_ve_plan_result_size(const bnpp_ve_plan *plan, uint64_t *n);
 /* BN::marginals (code/model.cpp:320-339) for EVERY variable in one plan: two passes over the
  * bucket tree of `order` (which must cover all unobserved variables) instead of one VE pass
  * per variable.  Run it with bnpp_ve_plan_run: result_dev receives, per variable id
@@ -196,11 +201,18 @@ int bnpp_ve_plan_run(bnpp_ve_plan *plan, const double *const *tables_dev, const 
 int bnpp_mar_plan_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfac, const bnpp_scope *scopes, int n_obs,
                          const uint32_t *obs_var, int n_order, const uint32_t *order, bnpp_ve_plan **out);
 int bnpp_mar_plan_layout(const bnpp_ve_plan *plan, int nvars, uint32_t *off, uint32_t *size, uint64_t *total);
+/* A marginals plan normalises every slice at the end of a run.  set_normalize(plan, 0) leaves the slices
+ * unnormalised (P(v, evidence) -- what a sharded run sums over the ranks before it normalises,
+ * bnpp_b200_nccl.h); bnpp_mar_plan_normalize then normalises a result buffer in place. */
+int bnpp_ve_plan_set_normalize(bnpp_ve_plan *plan, int on);
+int bnpp_mar_plan_normalize(bnpp_ve_plan *plan, double *result_dev);
 
 /* K8 -- the same plan for a BATCH of evidence sets (BASELINE config 5): ev_dev is a device
  * matrix [nb][n_obs] of evidence values (uint8, column j = obs_var[j] of the plan);
  * result_dev receives [result_size][nb] doubles, batch fastest (PR: one double per set).
- * One launch per bucket for the whole batch; CPTs are shared, never copied per set. */
+ * One launch per bucket for the whole batch; CPTs are shared, never copied per set.
+ * n_obs must equal the plan's; a value >= its variable's cardinality is treated as 0 and raises
+ * BNPP_STATUS_BAD_EVIDENCE (bnpp_ctx_status). */
 int bnpp_ve_plan_run_batched(bnpp_ve_plan *plan, const double *const *tables_dev, uint32_t nb, uint32_t n_obs,
                              const uint8_t *ev_dev, double *result_dev);
 /* K9 -- a plan whose elimination steps are all small (every union table <= 2^14 entries: the
@@ -254,8 +266,12 @@ int bnpp_fg_destroy(bnpp_fg *fg);
  * (NaN ignored, inf kept, code/graph.cpp:349-356).  Synchronises. */
 int bnpp_fg_sweep(bnpp_fg *fg, double *maxerror_host);
 /* FactorGraph::update(max, epsilon), code/graph.cpp:298-332: *sweeps receives the
- * 0-based index of the converging sweep, or max_sweeps. */
+ * 0-based index of the converging sweep, or max_sweeps.  The whole loop is ONE cooperative launch (both
+ * phases of every sweep separated by grid barriers, convergence test and sweep counter on the device); the
+ * host reads the count once.  Synchronises. */
 int bnpp_fg_update(bnpp_fg *fg, uint32_t max_sweeps, double epsilon, uint32_t *sweeps);
+/* messages back to the uniform start (code/graph.cpp:261-274), e.g. before a second update() */
+int bnpp_fg_reset(bnpp_fg *fg);
 /* FactorGraph::marginal for every variable (code/graph.cpp:393-403):
  * out_host[moff_var[v] .. +card[v]) with moff_var the exclusive prefix sum of card. */
 int bnpp_fg_marginals(bnpp_fg *fg, double *out_host);

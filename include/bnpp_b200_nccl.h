@@ -21,6 +21,19 @@ extern "C" {
  * nccl_comm is an ncclComm_t created by the caller (one rank per GPU). */
 int bnpp_shard_allreduce_sum(bnpp_ctx *ctx, void *nccl_comm, double *buf_dev, uint64_t n);
 
+/* BN::partition / variable_elimination / marginals of ONE network sharded over the ranks of nccl_comm
+ * (code/model.cpp:275-294, 320-339, 348-446; the reference has no multi-process form).  `plan` is this rank's
+ * bnpp_ve_plan (or marginals plan) created with the shard variables (bnpp_pick_shard_vars) among its
+ * observed ids, obs_val holds the evidence values and THIS RANK's values of the shard variables.  Every
+ * rank runs its slab, then the result tables (bnpp_ve_plan_result_size doubles: the scalar P(e) for a
+ * partition plan, a table over the kept variables otherwise) and *z_dev are summed over all ranks in place
+ * -- the cross-shard sum-out -- so every rank ends with the result of the unsharded query.  A marginals
+ * plan is run unnormalised, summed, then normalised; the slices of the shard variables themselves hold 1
+ * (each rank sees them observed): their marginals follow from the ranks' partitions.  Asynchronous on the
+ * context's stream. */
+int bnpp_ve_plan_run_sharded(bnpp_ctx *ctx, bnpp_ve_plan *plan, void *nccl_comm, const double *const *tables_dev,
+                             const uint32_t *obs_val, double *result_dev, double *z_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,7 +150,7 @@ def test_batch_one_launch(ctx, golden_synth):
         evs = synth.evidence_batch(rec["N"], rec["nobs"], nsets, seed=5, fixed_ids=True)
         observed = sorted(evs[0])
         zf, lf = _batch(bn, observed, evs, True)
-        assert lf == 1, lf
+        assert lf == 2, lf          # the evidence range check (sanitize_evidence) + ONE ve_fused launch
         zb, lb = _batch(bn, observed, evs, False)
         assert lb > 1
         assert np.array_equal(zf, zb), rec["N"]
@@ -158,7 +158,7 @@ def test_batch_one_launch(ctx, golden_synth):
             assert math.isclose(zf[i], rec["pr"][i], rel_tol=REL), (rec["N"], i)
         for lanes in (8, 16, 32, 128):
             zl, ll = _batch(bn, observed, evs, True, lanes)
-            assert ll == 1
+            assert ll == 2           # evidence check + the fused launch
             assert np.array_equal(zl, zf), (rec["N"], lanes)
         rng = random.Random(3)
         for i in rng.sample(range(nsets), 5) + [0, nsets - 1]:
@@ -175,7 +175,7 @@ def test_batch_large_one_launch(ctx):
     observed = sorted(evs[0])
     zf, lf = _batch(bn, observed, evs, True)
     zb, _ = _batch(bn, observed, evs, False)
-    assert lf == 1
+    assert lf == 2               # evidence check + the fused launch
     assert np.array_equal(zf, zb)
     assert np.all(zf > 0) and np.all(zf < 1)
     bn.close()
