@@ -168,6 +168,89 @@ __device__ __forceinline__ double entries_dispatch(const SetView<SPW> &v, const 
     return entries_any<K, G, SPW>(v, op, amask, tab, n_out, cx, lane, d);
 }
 
+// the steps of one program for one evidence set (b), on the G lanes that own it
+template <int G, int SPW>
+__device__ __forceinline__ void run_steps(const uint32_t *__restrict__ prog, const uint32_t *__restrict__ offtab, uint32_t n_steps,
+                                          const uint8_t *ev, double *result, double *zout, uint32_t nb, uint32_t b, bool live,
+                                          const SetView<SPW> &v, uint32_t lane, double *s_red)
+{
+    const uint32_t tw = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t pc = 0;
+    for (uint32_t s = 0; s < n_steps; ++s) {
+        const uint4 h0 = ldg4(prog + pc), h1 = ldg4(prog + pc + 4);
+        pc += kFusedHeaderWords;
+        const uint32_t n_out = h0.x, cx = h0.y, k = h0.z & 0xffu, flags = h0.z >> 8, tab_off = h1.x;
+        Dest d;
+        d.out_off = h0.w;
+        d.store = live;
+        if (flags & kFusedToResult) {
+            d.result = result + ((uint64_t)h0.w * nb + b);
+            d.stride = nb;
+        } else if (flags & kFusedToGlobal) {      // single queries inside a launch-per-bucket plan: a later launch reads it
+            d.result = reinterpret_cast<double *>(((uint64_t)h1.z << 32) | (uint64_t)h1.y);
+            d.stride = 1;
+        } else {
+            d.result = nullptr;
+            d.stride = 0;
+        }
+        // operand records (the k of a step is uniform over its lanes)
+        Operands op;
+        uint32_t amask = 0;
+#pragma unroll
+        for (int q = 0; q < kMaxK; ++q) {
+            if (q < (int)k) {
+                const uint4 r = ldg4(prog + pc);
+                pc += kFusedOperandWords;
+                op.sx[q] = r.z;
+                if ((r.x & 0xffu) == 0) {
+                    op.base[q] = r.y;
+                    op.cpt[q] = nullptr;
+                    amask |= 1u << q;
+                } else {
+                    const uint32_t nobs = r.x >> 8;
+                    uint32_t e = 0;
+                    for (uint32_t j = 0; j < nobs; j += 2) {
+                        const uint4 ob = ldg4(prog + pc);
+                        pc += 4;
+                        e += ob.x * ev[ob.y];
+                        if (j + 1 < nobs) e += ob.z * ev[ob.w];
+                    }
+                    op.base[q] = 0;
+                    op.cpt[q] = reinterpret_cast<const double *>(((uint64_t)r.w << 32) | (uint64_t)r.y) + e;
+                }
+            }
+        }
+        const uint32_t *tab = offtab + tab_off;
+        const bool pairs = (flags & kFusedPairs) != 0;
+        double zacc;
+        switch (k) {
+        case 1: zacc = entries_dispatch<1, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
+        case 2: zacc = entries_dispatch<2, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
+        case 3: zacc = entries_dispatch<3, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
+        case 4: zacc = entries_dispatch<4, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
+        case 5: zacc = entries_dispatch<5, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
+        default: zacc = entries_dispatch<6, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
+        }
+        if ((flags & kFusedWantZ) && zout) {      // uniform over the lanes of the set; only single queries ask for it
+            double z = zacc;
+            if (G <= 32) {
+                // the lanes of a set are the threads l * SPW + s of the warp
+#pragma unroll
+                for (int o = 16; o >= SPW; o >>= 1) z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, o));
+            } else {
+                z = warp_sum(z);
+                if (tw == 0) s_red[warp] = z;
+                __syncthreads();
+                z = 0.0;
+#pragma unroll
+                for (int i = 0; i < kFusedThreads / 32; ++i) z = __dadd_rn(z, s_red[i]);
+            }
+            if (lane == 0 && live) zout[b] = z;
+        }
+        group_sync<G>();     // the step's output is complete, and its operands are dead, before the next step
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(kFusedThreads) ve_fused(const __grid_constant__ FusedLaunch p)
 {
@@ -196,80 +279,23 @@ __global__ void __launch_bounds__(kFusedThreads) ve_fused(const __grid_constant_
         const bool live = b < p.nb;      // lanes of a missing set repeat the last one (they take part in the syncs), stores off
         if (!live) b = p.nb - 1;
         const uint8_t *ev = p.ev ? p.ev + (uint64_t)b * p.n_obs : p.ev_inline;
-        uint32_t pc = 0;
-        for (uint32_t s = 0; s < p.n_steps; ++s) {
-            const uint4 h0 = ldg4(p.prog + pc), h1 = ldg4(p.prog + pc + 4);
-            pc += kFusedHeaderWords;
-            const uint32_t n_out = h0.x, cx = h0.y, k = h0.z & 0xffu, flags = h0.z >> 8, tab_off = h1.x;
-            Dest d;
-            d.out_off = h0.w;
-            d.store = live;
-            if (flags & kFusedToResult) {
-                d.result = p.result + ((uint64_t)h0.w * p.nb + b);
-                d.stride = p.nb;
-            } else if (flags & kFusedToGlobal) {      // single queries inside a launch-per-bucket plan: a later launch reads it
-                d.result = reinterpret_cast<double *>(((uint64_t)h1.z << 32) | (uint64_t)h1.y);
-                d.stride = 1;
-            } else {
-                d.result = nullptr;
-                d.stride = 0;
-            }
-            // operand records (the k of a step is uniform over the grid)
-            Operands op;
-            uint32_t amask = 0;
-#pragma unroll
-            for (int q = 0; q < kMaxK; ++q) {
-                if (q < (int)k) {
-                    const uint4 r = ldg4(p.prog + pc);
-                    pc += kFusedOperandWords;
-                    op.sx[q] = r.z;
-                    if ((r.x & 0xffu) == 0) {
-                        op.base[q] = r.y;
-                        op.cpt[q] = nullptr;
-                        amask |= 1u << q;
-                    } else {
-                        const uint32_t nobs = r.x >> 8;
-                        uint32_t e = 0;
-                        for (uint32_t j = 0; j < nobs; j += 2) {
-                            const uint4 ob = ldg4(p.prog + pc);
-                            pc += 4;
-                            e += ob.x * ev[ob.y];
-                            if (j + 1 < nobs) e += ob.z * ev[ob.w];
-                        }
-                        op.base[q] = 0;
-                        op.cpt[q] = reinterpret_cast<const double *>(((uint64_t)r.w << 32) | (uint64_t)r.y) + e;
-                    }
-                }
-            }
-            const uint32_t *tab = p.offtab + tab_off;
-            const bool pairs = (flags & kFusedPairs) != 0;
-            double zacc;
-            switch (k) {
-            case 1: zacc = entries_dispatch<1, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
-            case 2: zacc = entries_dispatch<2, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
-            case 3: zacc = entries_dispatch<3, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
-            case 4: zacc = entries_dispatch<4, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
-            case 5: zacc = entries_dispatch<5, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
-            default: zacc = entries_dispatch<6, G, SPW>(v, op, amask, pairs, tab, n_out, cx, lane, d); break;
-            }
-            if ((flags & kFusedWantZ) && p.z) {      // uniform over the grid; only single queries ask for it
-                double z = zacc;
-                if (G <= 32) {
-                    // the lanes of a set are the threads l * SPW + s of the warp
-#pragma unroll
-                    for (int o = 16; o >= SPW; o >>= 1) z = __dadd_rn(z, __shfl_xor_sync(0xffffffffu, z, o));
-                } else {
-                    z = warp_sum(z);
-                    if (tw == 0) s_red[warp] = z;
-                    __syncthreads();
-                    z = 0.0;
-#pragma unroll
-                    for (int i = 0; i < kFusedThreads / 32; ++i) z = __dadd_rn(z, s_red[i]);
-                }
-                if (lane == 0 && live) p.z[b] = z;
-            }
-            group_sync<G>();     // the step's output is complete, and its operands are dead, before the next step
-        }
+        run_steps<G, SPW>(p.prog, p.offtab, p.n_steps, ev, p.result, p.z, p.nb, b, live, v, lane, s_red);
+    }
+}
+
+// K10 -- TASKS: one launch runs many independent programs of one query, a CTA each.  A mixed plan (hundreds of tiny
+// buckets around a few wide ones: Munin*, Link, Pigs, andes ...) is cut into tasks -- subtrees of the bucket tree whose
+// steps are all small -- and the tasks whose inputs are ready form one launch (ve.cu, build_levels); inside a task the
+// intermediates live in shared memory, its root's output goes to the plan's global arena.
+__global__ void __launch_bounds__(kFusedThreads) ve_tasks(const __grid_constant__ TaskLaunch p)
+{
+    __shared__ double s_red[kFusedThreads / 32];
+    SetView<1> v;
+    v.wbase = 0;
+    for (uint32_t t = blockIdx.x; t < p.n_tasks; t += gridDim.x) {
+        const uint4 task = ldg4(reinterpret_cast<const uint32_t *>(p.tasks + t));      // prog offset, offtab base, steps, arena
+        run_steps<128, 1>(p.prog + task.x, p.offtab + task.y, task.z, p.ev_inline, p.result, p.z, 1u, 0u, true, v, threadIdx.x, s_red);
+        __syncthreads();
     }
 }
 
@@ -295,8 +321,8 @@ int fused_launch(bnpp_ctx *ctx, int G, const FusedLaunch &p)
     }
     if (p.arena & 1u) return fail(ctx, BNPP_EINVAL, "fused VE: the arena of a set must be an even number of doubles");
     const size_t smem = fused_smem_bytes(G, p.arena);
-    static std::map<const void *, size_t> granted;      // dynamic shared memory opted into, per variant
-    size_t &have = granted[reinterpret_cast<const void *>(fn)];
+    static std::map<std::pair<int, const void *>, size_t> granted;      // dynamic shared memory opted into, per device and variant
+    size_t &have = granted[{ctx->device, reinterpret_cast<const void *>(fn)}];
     if (smem > have) {
         BNPP_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         have = smem;
@@ -318,6 +344,46 @@ int fused_launch(bnpp_ctx *ctx, int G, const FusedLaunch &p)
     ctx->last_desc = nullptr;
     ctx->last_kernel = G == 8 ? "ve_fused<G=8>" : (G == 16 ? "ve_fused<G=16>" : (G == 32 ? "ve_fused<G=32>" : "ve_fused<G=128>"));
     ctx->last_grid = (uint32_t)blocks;
+    ctx->last_block = kFusedThreads;
+    return BNPP_OK;
+}
+
+}  // namespace bnpp
+
+namespace bnpp {
+
+const void *tasks_kernel() { return reinterpret_cast<const void *>(ve_tasks); }
+
+// grid and dynamic shared memory of a ve_tasks launch over n_tasks programs whose largest arena is `arena` doubles
+int tasks_geometry(bnpp_ctx *ctx, uint32_t n_tasks, uint32_t arena, unsigned *grid, unsigned *smem)
+{
+    const size_t bytes = fused_smem_bytes(128, arena);
+    static std::map<std::pair<int, const void *>, size_t> granted;
+    size_t &have = granted[{ctx->device, tasks_kernel()}];
+    if (bytes > have) {
+        BNPP_CUDA(ctx, cudaFuncSetAttribute(ve_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        have = bytes;
+    }
+    int per_sm = 0;
+    BNPP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ve_tasks, kFusedThreads, bytes));
+    if (per_sm < 1) return fail(ctx, BNPP_ETOOBIG, "task launch: the arena of one task does not fit in shared memory");
+    uint64_t blocks = n_tasks;
+    const uint64_t resident = (uint64_t)ctx->sm_count * per_sm;
+    if (blocks > resident) blocks = resident;
+    if (blocks < 1) blocks = 1;
+    *grid = (unsigned)blocks;
+    *smem = (unsigned)bytes;
+    return BNPP_OK;
+}
+
+int tasks_launch(bnpp_ctx *ctx, const TaskLaunch &p, unsigned grid, unsigned smem)
+{
+    void *args[1] = {const_cast<TaskLaunch *>(&p)};
+    BNPP_CUDA(ctx, cudaLaunchKernel(tasks_kernel(), dim3(grid), dim3(kFusedThreads), args, smem, ctx->stream));
+    ctx->launches++;
+    ctx->last_desc = nullptr;
+    ctx->last_kernel = "ve_tasks";
+    ctx->last_grid = grid;
     ctx->last_block = kFusedThreads;
     return BNPP_OK;
 }

@@ -50,6 +50,26 @@ struct FusedLaunch {
     uint8_t ev_inline[kFusedInlineEv];
 };
 
+// K10: many independent programs of ONE query in one launch, a CTA (128 lanes) per program ("task")
+struct TaskRecord {
+    uint32_t prog_off;          // first word of the task's program in `prog`
+    uint32_t tab_base;          // first word of its operand-offset tables in `offtab`
+    uint32_t n_steps;
+    uint32_t arena;             // doubles of shared memory the task needs
+};
+struct TaskLaunch {
+    const uint32_t *prog;
+    const uint32_t *offtab;
+    const TaskRecord *tasks;    // device, 16-byte records
+    double *result;
+    double *z;
+    uint32_t n_tasks, n_obs;
+    uint8_t ev_inline[kFusedInlineEv];
+};
+const void *tasks_kernel();
+int tasks_geometry(bnpp_ctx *ctx, uint32_t n_tasks, uint32_t arena, unsigned *grid, unsigned *smem);
+int tasks_launch(bnpp_ctx *ctx, const TaskLaunch &p, unsigned grid, unsigned smem);
+
 // G = lanes per evidence set: 8, 16, 32 (a warp) or 128 (the CTA)
 bool fused_valid_g(int G);
 size_t fused_smem_bytes(int G, uint32_t arena);

@@ -106,14 +106,36 @@ struct bnpp_ve_plan {
     bool normalize = true;                  // marginals plan: normalise the slices at the end of a run
     int fused_mode = 1;                     // 0: one launch per bucket always; 1: one launch per plan when every step is small
     bnpp::FusedProgram fused;
-    // EXPERIMENTAL (off unless BNPP_FUSED_SEGMENTS=1 or bnpp_ve_plan_set_segments): inside a launch-per-bucket plan,
-    // every run of consecutive small steps is one ve_fused launch (DESIGN.md gap 4)
-    struct Segment { int a = 0, b = 0, G = 0; bnpp::FusedProgram prog; };
-    int segments_mode = 0;
-    uint32_t segments_max_steps = 0;        // > 0: cut runs into pieces of at most this many steps (tests)
-    bool segments_built = false;
+    // K10 -- TASKS (on unless BNPP_FUSED_SEGMENTS=0): a plan that is not one launch altogether is cut into tasks --
+    // subtrees of the bucket tree whose steps are all small, run by ONE CTA with their intermediates in shared memory
+    // (a "segment": a contiguous range of the re-ordered step list, with its own step program) -- and the tasks whose
+    // inputs are ready form ONE ve_tasks launch (a "group" = the small tasks of one dependency level).  Wide steps
+    // stay their own launches.  Hundreds of tiny launches become a few dozen.
+    struct Segment { int a = 0, b = 0, G = 128; int level = 0; bnpp::FusedProgram prog; };
+    struct Group {
+        int a = 0, b = 0;                   // step range covered (all its steps are small and of one level)
+        int first_seg = 0, n_segs = 0;
+        uint32_t max_arena = 0;
+        unsigned grid = 0, smem = 0;
+        bnpp::TaskLaunch launch;            // parameters of the launch (evidence and result pointers patched per run)
+        bool launch_valid = false;
+    };
+    int segments_mode = 1;
+    uint32_t segments_max_steps = 0;        // > 0: at most this many steps per task (tests)
+    bool segments_built = false, levels_built = false;
     std::vector<Segment> segs;
-    std::vector<int> seg_at;                // per step: the segment that STARTS here, or -1
+    std::vector<Group> groups;
+    std::vector<int> group_at;              // per step: the group that STARTS here, or -1
+    std::vector<int> step_level;            // per step (after build_levels): dependency level; steps of a level never read each other
+    std::vector<int> step_task;             // per step: root step of its task (small steps), -1 for wide steps
+    // all task programs of the plan in ONE device buffer each (one upload)
+    std::vector<uint32_t> tasks_prog, tasks_tab;
+    std::vector<bnpp::TaskRecord> tasks_rec;
+    struct TaskSlot { uint32_t lo, hi; int kind, index; uint64_t addr; };
+    std::vector<TaskSlot> tasks_slots;
+    uint32_t *tasks_prog_dev = nullptr, *tasks_tab_dev = nullptr;
+    bnpp::TaskRecord *tasks_rec_dev = nullptr;
+    bool tasks_uploaded = false;
     std::vector<bnpp::PlanFactor> f;
     std::vector<bnpp::PlanStep> steps;
     std::vector<uint32_t> result_var, result_card;
@@ -131,6 +153,7 @@ struct bnpp_ve_plan {
     // cudaGraphLaunch; only nodes whose pointers moved (other evidence values) are re-parameterised
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
+    bool graph_groups = false;              // the graph was built with task groups as nodes
     std::vector<cudaGraphNode_t> nodes;
     // batched replay: per-step operand-offset tables (host copy + device copy, built on first use)
     std::vector<std::vector<uint32_t>> offtab_host;
@@ -378,12 +401,22 @@ void build_exec(bnpp_ve_plan *pl)
             free_list.pop_back();
         }
     };
+    // steps of one dependency level may run concurrently (the tasks of a ve_tasks launch): what a level's steps read
+    // is released only when the level ends
+    std::vector<int> pending;
+    const bool leveled = pl->step_level.size() == pl->steps.size();
     for (size_t s = 0; s < pl->steps.size(); ++s) {
         const PlanStep &st = pl->steps[s];
         if (st.out >= 0) pl->arena_off[st.out] = take(pl->f[st.out].size);
         pl->arena_doubles = std::max(pl->arena_doubles, top);
         for (int id : st.operands)
-            if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) give(pl->arena_off[id], pl->f[id].size);
+            if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s && std::find(pending.begin(), pending.end(), id) == pending.end())
+                pending.push_back(id);
+        const bool level_ends = !leveled || s + 1 == pl->steps.size() || pl->step_level[s + 1] != pl->step_level[s];
+        if (level_ends) {
+            for (int id : pending) give(pl->arena_off[id], pl->f[id].size);
+            pending.clear();
+        }
     }
 
     // launches are resolved lazily, step by step, during the first run (plan_step): the GPU already
@@ -759,48 +792,240 @@ bool segments_default_on()
 {
     static const int on = [] {
         const char *e = getenv("BNPP_FUSED_SEGMENTS");
-        return (e && e[0] == '1') ? 1 : 0;
+        return (e && e[0] == '0') ? 0 : 1;
     }();
     return on != 0;
 }
 
-// runs of consecutive small steps, in plan order (single queries only)
+constexpr uint64_t kTaskMaxWork = 1ull << 16;       // union entries one task (one CTA) may walk: a few microseconds, like a launch
+
+bool step_is_small(const PlanStep &st)
+{
+    return st.union_entries <= kFusedMaxUnion && !st.operands.empty() && (int)st.operands.size() <= kMaxK;
+}
+
+void free_tasks(bnpp_ve_plan *pl)
+{
+    if (pl->tasks_prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->tasks_prog_dev));
+    if (pl->tasks_tab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->tasks_tab_dev));
+    if (pl->tasks_rec_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->tasks_rec_dev));
+    pl->tasks_prog_dev = pl->tasks_tab_dev = nullptr;
+    pl->tasks_rec_dev = nullptr;
+    pl->tasks_uploaded = false;
+    pl->tasks_prog.clear();
+    pl->tasks_tab.clear();
+    pl->tasks_rec.clear();
+    pl->tasks_slots.clear();
+    pl->segs.clear();
+    pl->groups.clear();
+    pl->group_at.clear();
+    pl->segments_built = false;
+}
+
+// Tasks and levels.  The steps of a plan form a DAG (a tree for PR plans).  A small step absorbs the tasks of its
+// small producers while the task stays within kTaskMaxWork (and segments_max_steps) and the producer's output has no
+// other reader -- such an intermediate then lives in the task's shared memory.  A task's level is one more than the
+// highest level it reads from; wide steps are levelled the same way.  The step list is re-ordered by (level, task),
+// which keeps it topological -- operand lists, hence the numbers, are untouched -- and the arena is laid out again
+// with level-wide lifetimes.  Only before the first run of a plan.
+void build_levels(bnpp_ve_plan *pl)
+{
+    if (pl->runs || pl->arena || pl->batch_runs || !pl->offtab_host.empty()) return;
+    const size_t ns = pl->steps.size();
+    free_tasks(pl);
+    pl->levels_built = true;
+    if (ns < 2) {
+        pl->step_level.assign(ns, 0);
+        pl->step_task.assign(ns, -1);
+        return;
+    }
+    std::vector<int> producer(pl->f.size(), -1), readers(pl->f.size(), 0);
+    for (size_t i = 0; i < ns; ++i) {
+        if (pl->steps[i].out >= 0) producer[pl->steps[i].out] = (int)i;
+        std::vector<int> seen;
+        for (int id : pl->steps[i].operands)
+            if (pl->f[id].src < 0 && std::find(seen.begin(), seen.end(), id) == seen.end()) {
+                seen.push_back(id);
+                readers[id]++;
+            }
+    }
+    std::vector<int> parent(ns, -1), level(ns, 0), nst(ns, 1);
+    std::vector<uint64_t> work(ns, 0);
+    std::vector<char> small(ns, 0);
+    for (size_t i = 0; i < ns; ++i) {
+        const PlanStep &st = pl->steps[i];
+        small[i] = step_is_small(st);
+        work[i] = st.union_entries;
+        std::vector<int> kids;
+        for (int id : st.operands) {
+            const int c = pl->f[id].src < 0 ? producer[id] : -1;
+            if (c >= 0 && std::find(kids.begin(), kids.end(), c) == kids.end()) kids.push_back(c);
+        }
+        std::stable_sort(kids.begin(), kids.end(), [&](int x, int y) { return work[x] < work[y]; });
+        for (int c : kids) {
+            // within the work budget -- or a chain link (the only producer this step waits for): cutting a chain buys no
+            // parallelism, only launches
+            const bool absorb = small[i] && small[c] && parent[c] < 0 && readers[pl->steps[c].out] == 1 &&
+                                (work[i] + work[c] <= kTaskMaxWork || (kids.size() == 1 && work[i] + work[c] <= 8 * kTaskMaxWork)) &&
+                                (!pl->segments_max_steps || (uint32_t)(nst[i] + nst[c]) <= pl->segments_max_steps);
+            if (absorb) {
+                parent[c] = (int)i;
+                work[i] += work[c];
+                nst[i] += nst[c];
+                level[i] = std::max(level[i], level[c]);
+            } else {
+                level[i] = std::max(level[i], level[c] + 1);
+            }
+        }
+    }
+    // root of every small step's task; a step absorbed into a task takes the task's level
+    std::vector<int> root(ns, -1);
+    for (size_t i = ns; i-- > 0;) {
+        if (!small[i]) continue;
+        root[i] = parent[i] >= 0 ? root[parent[i]] : (int)i;
+        if (parent[i] >= 0) level[i] = level[root[i]];
+    }
+    std::vector<size_t> order(ns);
+    for (size_t i = 0; i < ns; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+        if (level[x] != level[y]) return level[x] < level[y];
+        if (small[x] != small[y]) return small[x] > small[y];         // the level's tasks first, then its wide steps
+        if (small[x] && root[x] != root[y]) return root[x] < root[y];
+        return x < y;
+    });
+    std::vector<PlanStep> steps;
+    steps.reserve(ns);
+    std::vector<int> new_index(ns, -1);
+    pl->step_level.assign(ns, 0);
+    pl->step_task.assign(ns, -1);
+    for (size_t j = 0; j < ns; ++j) {
+        new_index[order[j]] = (int)j;
+        pl->step_level[j] = level[order[j]];
+    }
+    for (size_t j = 0; j < ns; ++j) {
+        pl->step_task[j] = small[order[j]] ? new_index[root[order[j]]] : -1;
+        steps.push_back(std::move(pl->steps[order[j]]));
+    }
+    pl->steps = std::move(steps);
+    for (PlanFactor &pf : pl->f) pf.last_use = -1;
+    for (size_t i = 0; i < ns; ++i)
+        for (int id : pl->steps[i].operands) pl->f[id].last_use = (int)i;
+    pl->arena_doubles = 0;
+    build_exec(pl);
+    pl->peak_bytes = 8 * pl->arena_doubles;
+    pl->exec.clear();
+    pl->exec_planned.clear();
+    if (pl->fused.prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.prog_dev));
+    if (pl->fused.offtab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.offtab_dev));
+    pl->fused = FusedProgram();
+}
+
+// the step program of every task, the groups (one ve_tasks launch each), and all programs in one buffer
 void build_segments(bnpp_ve_plan *pl)
 {
+    free_tasks(pl);
     pl->segments_built = true;
-    pl->segs.clear();
     const size_t ns = pl->steps.size();
-    pl->seg_at.assign(ns, -1);
-    auto small = [&](size_t s) {
-        const PlanStep &st = pl->steps[s];
-        return st.union_entries <= kFusedMaxUnion && !st.operands.empty() && (int)st.operands.size() <= kMaxK;
-    };
-    const size_t min_len = pl->segments_max_steps ? 1 : 2;
+    pl->group_at.assign(ns, -1);
+    if (!pl->levels_built || pl->step_task.size() != ns) return;
     size_t s = 0;
     while (s < ns) {
-        if (!small(s)) { ++s; continue; }
+        if (pl->step_task[s] < 0) { ++s; continue; }
+        // the small steps of one level are contiguous: [s, e)
         size_t e = s;
-        while (e < ns && small(e) && (!pl->segments_max_steps || e - s < pl->segments_max_steps)) ++e;
-        if (e - s >= min_len) {
+        while (e < ns && pl->step_task[e] >= 0 && pl->step_level[e] == pl->step_level[s]) ++e;
+        bnpp_ve_plan::Group g;
+        g.a = (int)s;
+        g.b = (int)e;
+        g.first_seg = (int)pl->segs.size();
+        bool ok = true;
+        for (size_t t = s; t < e && ok;) {
+            size_t u = t;
+            while (u < e && pl->step_task[u] == pl->step_task[t]) ++u;
             bnpp_ve_plan::Segment seg;
-            seg.a = (int)s;
-            seg.b = (int)e;
+            seg.a = (int)t;
+            seg.b = (int)u;
+            seg.level = pl->step_level[t];
             std::vector<int> order;
-            for (size_t i = s; i < e; ++i) order.push_back((int)i);
+            for (size_t i = t; i < u; ++i) order.push_back((int)i);
             fused_encode(pl, order, true, seg.prog);
-            if (seg.prog.ok) {
-                int G = seg.prog.max_out >= 128 ? 128 : 32;
-                if (fused_smem_bytes(G, seg.prog.arena) > kFusedSmemLimit) G = 128;
-                if (seg.prog.total_union / G > kFusedMaxLaneWork && G < 128) G = 128;
-                if (seg.prog.total_union / G <= kFusedMaxLaneWork && fused_smem_bytes(G, seg.prog.arena) <= kFusedSmemLimit) {
-                    seg.G = G;
-                    pl->seg_at[s] = (int)pl->segs.size();
-                    pl->segs.push_back(std::move(seg));
-                }
+            ok = seg.prog.ok && fused_smem_bytes(128, seg.prog.arena) <= kFusedSmemLimit;
+            if (ok) {
+                g.max_arena = std::max(g.max_arena, seg.prog.arena);
+                pl->segs.push_back(std::move(seg));
             }
+            t = u;
+        }
+        if (!ok) {
+            pl->segs.resize(g.first_seg);       // this level's small steps stay one launch each
+        } else {
+            g.n_segs = (int)pl->segs.size() - g.first_seg;
+            pl->group_at[s] = (int)pl->groups.size();
+            pl->groups.push_back(g);
         }
         s = e;
     }
+    // one buffer for all programs, one for all offset tables, one record per task
+    for (const auto &seg : pl->segs) {
+        TaskRecord r;
+        r.prog_off = (uint32_t)pl->tasks_prog.size();
+        r.tab_base = (uint32_t)pl->tasks_tab.size();
+        r.n_steps = seg.prog.n_steps;
+        r.arena = seg.prog.arena;
+        for (const auto &slot : seg.prog.ptr_slots)
+            pl->tasks_slots.push_back({slot.lo + r.prog_off, slot.hi + r.prog_off, slot.kind, slot.index, 0});
+        pl->tasks_prog.insert(pl->tasks_prog.end(), seg.prog.prog.begin(), seg.prog.prog.end());
+        pl->tasks_tab.insert(pl->tasks_tab.end(), seg.prog.offtab.begin(), seg.prog.offtab.end());
+        while (pl->tasks_tab.size() % 4) pl->tasks_tab.push_back(0);
+        pl->tasks_rec.push_back(r);
+    }
+}
+
+// device copies of the task programs; addresses inside them (CPT tables, arena slots) patched when they moved
+int upload_tasks(bnpp_ve_plan *pl, const double *const *tables_dev)
+{
+    bnpp_ctx *ctx = pl->ctx;
+    if (pl->segs.empty()) return BNPP_OK;
+    bool moved = !pl->tasks_uploaded;
+    for (auto &slot : pl->tasks_slots) {
+        const uint64_t a = slot.kind == 0 ? reinterpret_cast<uint64_t>(tables_dev[slot.index])
+                                          : reinterpret_cast<uint64_t>(pl->arena + pl->arena_off[slot.index]);
+        if (a != slot.addr) {
+            slot.addr = a;
+            pl->tasks_prog[slot.lo] = (uint32_t)a;
+            pl->tasks_prog[slot.hi] = (uint32_t)(a >> 32);
+            moved = true;
+        }
+    }
+    if (!pl->tasks_prog_dev) {
+        double *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+        int rc = bnpp_alloc(ctx, pl->tasks_prog.size() / 2 + 2, &p0);
+        if (rc == BNPP_OK) rc = bnpp_alloc(ctx, pl->tasks_tab.size() / 2 + 2, &p1);
+        if (rc == BNPP_OK) rc = bnpp_alloc(ctx, pl->tasks_rec.size() * 2 + 2, &p2);
+        if (rc != BNPP_OK) return rc;
+        pl->tasks_prog_dev = reinterpret_cast<uint32_t *>(p0);
+        pl->tasks_tab_dev = reinterpret_cast<uint32_t *>(p1);
+        pl->tasks_rec_dev = reinterpret_cast<TaskRecord *>(p2);
+        if (!pl->tasks_tab.empty())
+            BNPP_CUDA(ctx, cudaMemcpyAsync(pl->tasks_tab_dev, pl->tasks_tab.data(), pl->tasks_tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        BNPP_CUDA(ctx, cudaMemcpyAsync(pl->tasks_rec_dev, pl->tasks_rec.data(), pl->tasks_rec.size() * sizeof(TaskRecord), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (moved)      // stream-ordered after any launch still reading the previous contents; the pageable source is staged before the call returns
+        BNPP_CUDA(ctx, cudaMemcpyAsync(pl->tasks_prog_dev, pl->tasks_prog.data(), pl->tasks_prog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    pl->tasks_uploaded = true;
+    for (auto &g : pl->groups) {
+        if (g.launch_valid) continue;
+        const int rc = tasks_geometry(ctx, (uint32_t)g.n_segs, g.max_arena, &g.grid, &g.smem);
+        if (rc != BNPP_OK) return rc;
+        memset(&g.launch, 0, sizeof g.launch);
+        g.launch.prog = pl->tasks_prog_dev;
+        g.launch.offtab = pl->tasks_tab_dev;
+        g.launch.tasks = pl->tasks_rec_dev + g.first_seg;
+        g.launch.n_tasks = (uint32_t)g.n_segs;
+        g.launch.n_obs = (uint32_t)pl->n_obs;
+        g.launch_valid = true;
+    }
+    return BNPP_OK;
 }
 
 int run_fused(bnpp_ve_plan *pl, FusedProgram &fp, int G, const double *const *tables_dev, uint32_t nb, const uint8_t *ev_dev,
@@ -861,53 +1086,6 @@ int run_fused(bnpp_ve_plan *pl, FusedProgram &fp, int G, const double *const *ta
     if (!ev_dev && obs_val)
         for (int i = 0; i < pl->n_obs && i < kFusedInlineEv; ++i) p.ev_inline[i] = (uint8_t)obs_val[i];
     return fused_launch(ctx, G, p);
-}
-
-// Segments want long runs of small steps, a min-fill order interleaves small buckets with wide ones.  Any
-// topological order of the steps gives the same numbers (operand lists are untouched), so: first every small step all
-// of whose inputs are CPTs or outputs of such steps, in their old relative order, then the rest in theirs (the result
-// step stays last).  The arena is laid out again for the new lifetimes.  Only before the first run of a PR plan.
-void reorder_small_first(bnpp_ve_plan *pl)
-{
-    if (pl->is_mar || pl->runs || pl->arena || pl->steps.size() < 3) return;
-    const size_t ns = pl->steps.size();
-    std::vector<int> producer(pl->f.size(), -1);
-    for (size_t s = 0; s < ns; ++s)
-        if (pl->steps[s].out >= 0) producer[pl->steps[s].out] = (int)s;
-    std::vector<char> early(ns, 0);
-    size_t n_early = 0;
-    for (size_t s = 0; s < ns; ++s) {
-        const PlanStep &st = pl->steps[s];
-        bool e = st.out >= 0 && st.union_entries <= kFusedMaxUnion && !st.operands.empty() && (int)st.operands.size() <= kMaxK;
-        for (int id : st.operands)
-            if (e && pl->f[id].src < 0) e = producer[id] >= 0 && producer[id] < (int)s && early[producer[id]];
-        early[s] = e;
-        n_early += e;
-    }
-    if (n_early == 0 || n_early == ns) return;
-    std::vector<PlanStep> steps;
-    steps.reserve(ns);
-    for (int pass = 1; pass >= 0; --pass)
-        for (size_t s = 0; s < ns; ++s)
-            if (early[s] == pass) steps.push_back(std::move(pl->steps[s]));
-    pl->steps = std::move(steps);
-    for (PlanFactor &pf : pl->f) pf.last_use = -1;
-    uint64_t live = 0;
-    pl->peak_bytes = 0;
-    for (size_t s = 0; s < ns; ++s)
-        for (int id : pl->steps[s].operands) pl->f[id].last_use = (int)s;
-    for (size_t s = 0; s < ns; ++s) {
-        const PlanStep &st = pl->steps[s];
-        if (st.out >= 0) live += 8 * pl->f[st.out].size;
-        pl->peak_bytes = std::max(pl->peak_bytes, live);
-        for (int id : st.operands)
-            if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) live -= 8 * pl->f[id].size;
-    }
-    pl->arena_doubles = 0;
-    build_exec(pl);
-    pl->exec.clear();
-    pl->exec_planned.clear();
-    pl->fused = FusedProgram();
 }
 
 }  // namespace
@@ -984,7 +1162,7 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
             if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) live -= 8 * pl->f[id].size;
     }
     build_exec(pl);
-    if (pl->segments_mode) reorder_small_first(pl);
+    if (pl->segments_mode) build_levels(pl);
     *out = pl;
     return BNPP_OK;
 }
@@ -1103,6 +1281,7 @@ int bnpp_mar_plan_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfa
             if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) live -= 8 * pl->f[id].size;
     }
     build_exec(pl);
+    if (pl->segments_mode) build_levels(pl);
     if (!ctx) {
         *out = pl;
         return BNPP_OK;
@@ -1151,10 +1330,7 @@ int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
     if (pl->ctx && pl->ctx->last_desc && !pl->exec.empty() && pl->ctx->last_desc >= (void *)&pl->exec.front() &&
         pl->ctx->last_desc <= (void *)&pl->exec.back())
         pl->ctx->last_desc = nullptr;       // bnpp_last_launch must not follow a pointer into a dead plan
-    for (auto &seg : pl->segs) {
-        if (seg.prog.prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(seg.prog.prog_dev));
-        if (seg.prog.offtab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(seg.prog.offtab_dev));
-    }
+    free_tasks(pl);
     if (pl->fused.prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.prog_dev));
     if (pl->fused.offtab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.offtab_dev));
     if (pl->mar_off_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->mar_off_dev));
@@ -1299,15 +1475,17 @@ int bnpp_ve_plan_describe(const bnpp_ve_plan *pl, uint64_t *buf, uint64_t cap, u
 int bnpp_ve_plan_set_segments(bnpp_ve_plan *pl, int on, uint32_t max_steps)
 {
     if (!pl) return BNPP_EINVAL;
-    if (on) reorder_small_first(pl);
     pl->segments_mode = on != 0;
-    pl->segments_max_steps = max_steps;
-    pl->segments_built = false;
-    for (auto &seg : pl->segs) {
-        if (seg.prog.prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(seg.prog.prog_dev));
-        if (seg.prog.offtab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(seg.prog.offtab_dev));
+    if (pl->graph_exec && pl->graph_groups != (on != 0)) {      // the replay graph was built the other way
+        cudaGraphExecDestroy(pl->graph_exec);
+        cudaGraphDestroy(pl->graph);
+        pl->graph_exec = nullptr;
+        pl->graph = nullptr;
     }
-    pl->segs.clear();
+    if (on && (!pl->levels_built || max_steps != pl->segments_max_steps)) {
+        pl->segments_max_steps = max_steps;
+        build_levels(pl);       // re-orders the steps; refused (the plan keeps its tasks) once the plan has run
+    }
     return BNPP_OK;
 }
 
@@ -1344,6 +1522,20 @@ int bnpp_ve_plan_segments(bnpp_ve_plan *pl, uint32_t cap, uint32_t *n, uint32_t 
         if (lanes) lanes[i] = pl->segs[i].G;
         if (arena_doubles) arena_doubles[i] = pl->segs[i].prog.arena;
     }
+    return BNPP_OK;
+}
+
+// kernel launches of one single-query run with tasks on: one per group (all small tasks of a dependency level) plus
+// one per wide step; and the number of dependency levels
+int bnpp_ve_plan_launches(bnpp_ve_plan *pl, uint64_t *launches, uint32_t *groups, uint32_t *levels)
+{
+    if (!pl) return BNPP_EINVAL;
+    if (!pl->segments_built) build_segments(pl);
+    uint64_t covered = 0;
+    for (const auto &g : pl->groups) covered += (uint64_t)(g.b - g.a);
+    if (launches) *launches = pl->steps.size() - covered + pl->groups.size();
+    if (groups) *groups = (uint32_t)pl->groups.size();
+    if (levels) *levels = pl->step_level.empty() ? 0u : (uint32_t)(pl->step_level.back() + 1);
     return BNPP_OK;
 }
 
@@ -1497,21 +1689,54 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
         }
         for (size_t i = 0; i < pl->f.size(); ++i)
             if (pl->f[i].src < 0) ptr[i] = pl->arena + pl->arena_off[i];
-        // experimental: runs of consecutive small steps as one ve_fused launch each (plain launches, no graph)
-        const bool seg_on = pl->segments_mode && ev_inline && !pl->profiling;
+        // K10: the small tasks of every dependency level as ONE ve_tasks launch (a node of the replay graph like any other)
+        const bool seg_on = pl->segments_mode && pl->levels_built && ev_inline && !pl->profiling;
         if (seg_on && !pl->segments_built) build_segments(pl);
-        const bool graphed = pl->use_graph && !pl->profiling && pl->steps.size() > 1 && pl->runs >= 1 && !seg_on;
+        const bool use_groups = seg_on && !pl->groups.empty();
+        if (use_groups) {
+            rc = upload_tasks(pl, tables_dev);
+            if (rc != BNPP_OK) return rc;
+        }
+        const bool graphed = pl->use_graph && !pl->profiling && pl->steps.size() > 1 && pl->runs >= 1 &&
+                             (!pl->graph_exec || pl->graph_groups == use_groups);
         bool fresh = false;
         if (graphed && !pl->graph_exec) {
             if (cudaGraphCreate(&pl->graph, 0) != cudaSuccess) pl->use_graph = false;
             pl->nodes.assign(pl->steps.size(), nullptr);
+            pl->graph_groups = use_groups;
             fresh = true;
         }
+        cudaGraphNode_t prev = nullptr;
+        uint64_t n_launched = 0;
         for (size_t s = 0; s < pl->steps.size() && rc == BNPP_OK; ++s) {
-            if (seg_on && pl->seg_at[s] >= 0) {
-                bnpp_ve_plan::Segment &sg = pl->segs[pl->seg_at[s]];
-                rc = run_fused(pl, sg.prog, sg.G, tables_dev, 1, nullptr, obs_val, result_dev, z_dev);
-                s = (size_t)sg.b - 1;
+            if (use_groups && pl->group_at[s] >= 0) {
+                bnpp_ve_plan::Group &g = pl->groups[pl->group_at[s]];
+                TaskLaunch now = g.launch;
+                now.result = result_dev;
+                now.z = z_dev;
+                memset(now.ev_inline, 0, sizeof now.ev_inline);
+                for (int i = 0; i < pl->n_obs && i < kFusedInlineEv; ++i) now.ev_inline[i] = (uint8_t)obs_val[i];
+                const bool changed = fresh || memcmp(&now, &g.launch, sizeof now) != 0;
+                g.launch = now;
+                ++n_launched;
+                if (!(graphed && pl->use_graph)) {
+                    rc = tasks_launch(ctx, g.launch, g.grid, g.smem);
+                } else if (changed) {
+                    void *args[1] = {&g.launch};
+                    cudaKernelNodeParams kp;
+                    memset(&kp, 0, sizeof kp);
+                    kp.func = const_cast<void *>(tasks_kernel());
+                    kp.gridDim = dim3(g.grid);
+                    kp.blockDim = dim3(kFusedThreads);
+                    kp.sharedMemBytes = g.smem;
+                    kp.kernelParams = args;
+                    cudaError_t e;
+                    if (fresh) e = cudaGraphAddKernelNode(&pl->nodes[s], pl->graph, prev ? &prev : nullptr, prev ? 1 : 0, &kp);
+                    else e = cudaGraphExecKernelNodeSetParams(pl->graph_exec, pl->nodes[s], &kp);
+                    if (e != cudaSuccess) return cuda_fail(ctx, e, "CUDA graph node (tasks)");
+                }
+                if (fresh) prev = pl->nodes[s];
+                s = (size_t)g.b - 1;
                 continue;
             }
             const PlanStep &st = pl->steps[s];
@@ -1521,6 +1746,7 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             double *dst = st.out == -2 ? result_dev + st.roff : pl->arena + pl->arena_off[st.out];
             double *z = (st.out == -2 && st.want_z) ? z_dev : nullptr;
             if (!pl->exec_planned[s] && !plan_step(pl, s)) return fail(ctx, BNPP_EINVAL, "VE plan: a step could not be resolved");
+            ++n_launched;
             if (!(graphed && pl->use_graph)) {
                 rc = contract_launch(ctx, pl->exec[s], in, dst, z);
                 continue;
@@ -1543,16 +1769,17 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             kp.sharedMemBytes = d.smem;
             kp.kernelParams = args;
             cudaError_t e;
-            if (fresh) e = cudaGraphAddKernelNode(&pl->nodes[s], pl->graph, s ? &pl->nodes[s - 1] : nullptr, s ? 1 : 0, &kp);
+            if (fresh) e = cudaGraphAddKernelNode(&pl->nodes[s], pl->graph, prev ? &prev : nullptr, prev ? 1 : 0, &kp);
             else e = cudaGraphExecKernelNodeSetParams(pl->graph_exec, pl->nodes[s], &kp);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "CUDA graph node");
+            if (fresh) prev = pl->nodes[s];
         }
         if (graphed && pl->use_graph && rc == BNPP_OK) {
             if (fresh) BNPP_CUDA(ctx, cudaGraphInstantiate(&pl->graph_exec, pl->graph, 0));
             BNPP_CUDA(ctx, cudaGraphLaunch(pl->graph_exec, ctx->stream));
-            ctx->launches += pl->steps.size();
-            ctx->last_desc = &pl->exec.back();
-            ctx->last_kernel.clear();
+            ctx->launches += n_launched;
+            ctx->last_desc = nullptr;
+            ctx->last_kernel = "cudaGraphLaunch (VE plan replay)";
         }
         if (pl->profiling) {
             pl->step_kernel.resize(pl->steps.size());

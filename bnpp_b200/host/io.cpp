@@ -1,7 +1,10 @@
 #include "io.hh"
 #include "uai_parse.hpp"
 
+#include <algorithm>
+#include <cmath>
 #include <iostream>
+#include <vector>
 
 namespace bn {
 
@@ -143,6 +146,47 @@ int read_uai_evidence(std::string &filename, std::unordered_map<unsigned,unsigne
         }
     }
     return 0;
+}
+
+int write_uai_pr(const std::string &filename, double partition)
+{
+    std::ofstream out(filename);
+    if (!out.is_open()) return -1;
+    out << "PR" << std::endl << 1 << std::endl << std::log10(partition) << std::endl;
+    return out.good() ? 0 : -1;
+}
+
+int write_uai_mar(const std::string &filename, const std::vector<const Factor*> &marginals,
+                  const std::vector<unsigned> &cardinalities, const std::unordered_map<unsigned,unsigned> &evidence)
+{
+    std::ofstream out(filename);
+    if (!out.is_open()) return -1;
+    out << "MAR" << std::endl << 1 << std::endl << marginals.size() << std::endl;
+    for (size_t v = 0; v < marginals.size(); ++v) {
+        const unsigned card = v < cardinalities.size() ? cardinalities[v] : marginals[v]->size();
+        out << card;
+        const auto e = evidence.find((unsigned)v);
+        if (e != evidence.end() || marginals[v]->size() != card) {
+            // observed (BN::marginals / Model::marginals hand back the width-0 factor [1]): the indicator of its value
+            for (unsigned i = 0; i < card; ++i) out << ' ' << ((e != evidence.end() && e->second == i) ? 1 : 0);
+        } else {
+            for (unsigned i = 0; i < card; ++i) out << ' ' << (*marginals[v])[i];
+        }
+        out << std::endl;
+    }
+    return out.good() ? 0 : -1;
+}
+
+int write_uai_evidence(const std::string &filename, const std::unordered_map<unsigned,unsigned> &evidence)
+{
+    std::ofstream out(filename);
+    if (!out.is_open()) return -1;
+    std::vector<std::pair<unsigned,unsigned>> ev(evidence.begin(), evidence.end());
+    std::sort(ev.begin(), ev.end());
+    out << 1 << std::endl << ev.size();
+    for (const auto &e : ev) out << ' ' << e.first << ' ' << e.second;
+    out << std::endl;
+    return out.good() ? 0 : -1;
 }
 
 }  // namespace bn

@@ -16,6 +16,7 @@ using namespace std;
 static unordered_map<string,bool> options;
 static MN *model;
 static unordered_map<unsigned,unsigned> evidence;
+static string solution_prefix;      // -o <prefix>: PR / MAR also go to <prefix>.PR / <prefix>.MAR (UAI solution files)
 
 static void usage(const char *progname)
 {
@@ -30,16 +31,20 @@ static void read_options(int argc, char *argv[])
     static const char *flags[][2] = {{"-h", "help"}, {"-v", "verbose"}, {"-ve", "variable-elimination"},
                                      {"-mf", "min-fill"}, {"-wmf", "weighted-min-fill"}, {"-md", "min-degree"}};
     for (auto &f : flags) options[f[1]] = false;
-    for (int i = 2; i < argc; ++i)
+    for (int i = 2; i < argc; ++i) {
+        if (string(argv[i]) == "-o" && i + 1 < argc) solution_prefix = argv[++i];
         for (auto &f : flags)
             if (string(argv[i]) == f[0]) options[f[1]] = true;
+    }
 }
 
 static void execute_partition()
 {
     double uptime;
-    const double p = log10(model->partition(evidence, options, uptime));
+    const double z = model->partition(evidence, options, uptime);
+    const double p = log10(z);
     cout << "Partition = " << p << endl << endl;
+    if (!solution_prefix.empty() && write_uai_pr(solution_prefix + ".PR", z)) cerr << "Error: cannot write " << solution_prefix << ".PR" << endl;
     cout << ">> Executed in " << uptime << "ms." << endl << endl;
 }
 
@@ -48,6 +53,11 @@ static void execute_marginals()
     cout << ">> Marginals:" << endl;
     double uptime;
     vector<const Factor*> marginals = model->marginals(evidence, options, uptime);
+    if (!solution_prefix.empty()) {
+        vector<unsigned> cards;
+        for (const Variable *v : model->variables()) cards.push_back(v->size());
+        if (write_uai_mar(solution_prefix + ".MAR", marginals, cards, evidence)) cerr << "Error: cannot write " << solution_prefix << ".MAR" << endl;
+    }
     for (const Factor *pf : marginals) {
         cout << *pf << endl;
         delete pf;

@@ -235,14 +235,19 @@ int bnpp_ve_plan_fused_program(bnpp_ve_plan *plan, uint32_t nb, uint32_t *prog, 
  * lifetimes) on dry plans; the word stream is documented at the definition in bnpp_b200/csrc/ve.cu.  Pass buf = NULL
  * to query the size. */
 int bnpp_ve_plan_describe(const bnpp_ve_plan *plan, uint64_t *buf, uint64_t cap, uint64_t *words);
-/* EXPERIMENTAL, off by default (environment BNPP_FUSED_SEGMENTS=1 turns it on for new plans): inside a plan that
- * runs one launch per bucket, every run of consecutive small steps becomes ONE ve_fused launch (single queries);
- * max_steps > 0 cuts the runs into pieces of at most that many steps (tests).  _segments lists the step ranges,
- * _segment_program dumps one segment's program like _fused_program (0xfffffffe in an address's high word: the
- * intermediate with that index in the plan's global arena). */
+/* K10 -- TASKS, on by default (environment BNPP_FUSED_SEGMENTS=0 turns it off for new plans): a plan that is not one
+ * launch altogether (K9) is cut into tasks -- subtrees of the bucket tree whose steps are all small, each run by one
+ * CTA with its intermediates in shared memory -- and all tasks of one dependency level form ONE launch (ve_tasks);
+ * wide steps stay their own launches, and every launch is a node of the replay graph.  Replaces the loop of
+ * code/model.cpp:409-439 for mixed plans (Munin*, Link, Pigs, andes: ~1000 tiny buckets -> a few dozen launches).
+ * set_segments(plan, on, max_steps): max_steps > 0 limits the steps per task (tests); only before the first run can
+ * the tasks be re-cut.  _segments lists the tasks (a contiguous step range each), _segment_program dumps one task's
+ * program like _fused_program (0xfffffffe in an address's high word: the intermediate with that index in the plan's
+ * global arena), _launches counts the kernel launches of a single-query run. */
 int bnpp_ve_plan_set_segments(bnpp_ve_plan *plan, int on, uint32_t max_steps);
 int bnpp_ve_plan_segments(bnpp_ve_plan *plan, uint32_t cap, uint32_t *n, uint32_t *first_step, uint32_t *end_step,
                           int32_t *lanes, uint32_t *arena_doubles);
+int bnpp_ve_plan_launches(bnpp_ve_plan *plan, uint64_t *launches, uint32_t *groups, uint32_t *levels);
 int bnpp_ve_plan_segment_program(bnpp_ve_plan *plan, uint32_t segment, uint32_t *prog, uint64_t prog_cap, uint64_t *prog_words,
                                  uint32_t *offtab, uint64_t tab_cap, uint64_t *tab_words);
 /* per-launch CUDA-event timing for roofline reports: enable, run, then read

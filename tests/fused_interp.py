@@ -92,6 +92,14 @@ class DryPlan:
             out.append((a[i], b[i], g[i], ar[i], prog[:np_.value], tab[:nt.value]))
         return out
 
+    def launches(self):
+        """-> (kernel launches of a single-query run with tasks on, groups, dependency levels)"""
+        L = self.L
+        L.bnpp_ve_plan_launches.argtypes = [ctypes.c_void_p, capi.c_u64p, capi.c_u32p, capi.c_u32p]
+        n, g, lv = ctypes.c_uint64(), ctypes.c_uint32(), ctypes.c_uint32()
+        assert L.bnpp_ve_plan_launches(self.h, ctypes.byref(n), ctypes.byref(g), ctypes.byref(lv)) == 0
+        return n.value, g.value, lv.value
+
     def n_steps(self):
         vals = [ctypes.c_uint64() for _ in range(5)]
         assert self.L.bnpp_ve_plan_info(self.h, None, None, None, *[ctypes.byref(v) for v in vals]) == 0

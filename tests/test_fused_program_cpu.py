@@ -263,5 +263,5 @@ def test_segments_of_a_mixed_plan():
     steps = p.n_steps()
     covered = sum(end - first for first, end, *_ in segs)
     assert segs and 0 < covered < steps
-    assert all(end - first >= 2 for first, end, *_ in segs)
+    assert all(lanes == 128 for _, _, lanes, *_ in segs)
     p.close()

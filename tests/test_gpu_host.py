@@ -218,3 +218,31 @@ def test_cli_all_shipped_networks_side_by_side():
     out = subprocess.run([os.path.join(BIN, "mn"), net, os.path.join(MODELS, "markovnets", "network.uai.evid"), "-ve", "-mf"],
                          input="PR\nquit\n", capture_output=True, text=True, timeout=300)
     assert "Partition = 163.204" in out.stdout, out.stdout[-300:]
+
+
+def test_uai_solution_writers_round_trip(tmp_path):
+    """`mn ... -o prefix` writes prefix.PR / prefix.MAR in the UAI solution format; token for token the
+    files shipped beside the reference's models (models/markovnets/grid3x3.uai.PR, grid3x3.uai.MAR, network.uai.PR and
+    network.uai.MAR -- the latter two through VE, the brute-force joint of 2^120 entries is out of reach)"""
+    mk = os.path.join(MODELS, "markovnets")
+    if not os.path.isdir(mk):
+        pytest.skip("oracle/_ref/models not present")
+
+    def solve(model, evid, flags, command, suffix):
+        prefix = str(tmp_path / (model + suffix))
+        out = subprocess.run([os.path.join(BIN, "mn"), os.path.join(mk, model), os.path.join(mk, evid)] + flags + ["-o", prefix],
+                             input=command + "\nquit\n", capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-400:]
+        return open(prefix + "." + command).read().split()
+
+    def same(got, want_path):
+        want = open(want_path).read().split()
+        assert len(got) == len(want), (got[:12], want[:12])
+        for a, b in zip(got, want):
+            assert a == b or math.isclose(float(a), float(b), rel_tol=2e-5, abs_tol=1e-9), (a, b, want_path)
+
+    same(solve("grid3x3.uai", "grid3x3-PR.uai.evid", [], "PR", ""), os.path.join(mk, "grid3x3.uai.PR"))
+    same(solve("grid3x3.uai", "grid3x3-MAR.uai.evid", [], "MAR", ""), os.path.join(mk, "grid3x3.uai.MAR"))
+    same(solve("grid3x3.uai", "grid3x3-PR.uai.evid", ["-ve", "-mf"], "PR", ".ve"), os.path.join(mk, "grid3x3.uai.PR"))
+    same(solve("network.uai", "network.uai.evid", ["-ve", "-mf"], "PR", ""), os.path.join(mk, "network.uai.PR"))
+    same(solve("network.uai", "network.uai.evid", ["-ve", "-mf"], "MAR", ""), os.path.join(mk, "network.uai.MAR"))

@@ -1,15 +1,14 @@
-"""EXPERIMENTAL, skipped unless BNPP_TEST_EXPERIMENTAL=1 (DESIGN.md gap 4; first device run is the next round's):
-inside a launch-per-bucket plan, every run of consecutive small steps as ONE ve_fused launch.  The host half (the
-segment programs, their traffic through the plan's global arena) is pinned on the CPU by
+"""K10 (tasks): inside a plan that is not one launch altogether, the small steps are cut into tasks (subtrees of the
+bucket tree, one CTA each, intermediates in shared memory) and all tasks of a dependency level run as ONE ve_tasks
+launch.  The host half (the task programs, their traffic through the plan's global arena) is pinned on the CPU by
 tests/test_fused_program_cpu.py::test_segment_programs_chain_through_the_global_arena; this is the device half:
-results bit-identical to the plain launch-per-bucket run, fewer launches."""
+results bit-identical to the plain launch-per-bucket run, far fewer launches, also when replayed as a CUDA graph."""
 import math
 import os
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("BNPP_TEST_EXPERIMENTAL") != "1", reason="experimental path, off by default")]
+pytestmark = pytest.mark.gpu
 
 from bnpp_b200 import synth  # noqa: E402
 
@@ -62,3 +61,30 @@ def test_segments_on_the_wide_synthetic_network(ctx):
     assert z1 == z0 and l1 < l0
     assert math.isclose(z0, 1.0, rel_tol=1e-9)
     bn.close()
+
+
+def test_tasks_are_the_default_and_replay_as_a_graph(ctx, golden_models):
+    """default settings: Water / andes / insurance plans run as a handful of launches, and the graph replays (runs 2..4)
+    give the same bits as the first run and as one launch per bucket"""
+    from bnpp_b200 import model
+    for name in ["Water", "andes", "insurance"]:
+        m = golden_models[name]
+        bn = model.from_uai_text(ctx, m["uai"])[1]
+        case = [c for c in m["pr"] if c["flag"] == "mf"][-1]
+        ev = {int(k): v for k, v in case["evidence"].items()}
+        zs = []
+        for run in range(4):
+            ctx.sync()
+            l0 = ctx.launches
+            z, _ = bn.partition(ev, "mf")
+            zs.append(z)
+            launches = ctx.launches - l0
+        variables = [v for v in range(bn.nvars) if v not in ev]
+        order, _ = bn.order(variables, ev, "mf")
+        p = bn.plan(sorted(ev), order)
+        assert launches < p.n_launches / 2, (name, launches, p.n_launches)
+        p.set_segments(False, 0)
+        z_plain, _ = bn.partition(ev, "mf")
+        assert all(z == z_plain for z in zs), (name, zs, z_plain)
+        assert math.isclose(z_plain, case["pr"], rel_tol=1e-9)
+        bn.close()

@@ -104,3 +104,15 @@ def test_fast_uai_reader_equals_reference_reader(tmp_path, golden_models):
     for name in ("plus.uai", "subnormal.uai", "huge.uai", "hexfloat.uai", "junk_int.uai", "truncated.uai", "bad_scope.uai",
                  "header.uai", "empty.uai"):
         assert rows[name] == "FALLBACK", (name, rows[name])
+
+
+def test_uai_solution_writers_cpu(tmp_path):
+    """SURVEY 8f row 3 without a device: write_uai_pr gives the shipped grid3x3.uai.PR byte for byte (PR / 1 / 14.8899,
+    6 significant digits of log10 Z), write_uai_evidence round-trips through read_uai_evidence (code/io.cpp:157-180)"""
+    exe = os.path.join(ROOT, "tests", "bin", "uai_write_check")
+    if not os.path.exists(exe):
+        pytest.skip("uai_write_check not built (run build())")
+    out = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout == "PR\n1\n14.8899\n--\n1\n3 0 1 4 1 5 1\n--\nroundtrip ok\n", out.stdout
+    assert open(str(tmp_path / "w.PR")).read().split() == ["PR", "1", "14.8899"]

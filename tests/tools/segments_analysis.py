@@ -17,7 +17,7 @@ from fused_interp import DryPlan, parse_uai  # noqa: E402
 
 SMALL = 1 << 14
 print("| network | variables | min-fill width | order ms (host, this container) | plan ms (host) | launches | small launches | share of union entries in small steps | "
-      "K9 today | launches if small runs fused (elimination order) | launches, segment builder (small steps first) |")
+      "K9 today | launches if small runs fused (elimination order) | launches with tasks (K10: one launch per dependency level + wide steps) |")
 print("|---|---:|---:|---:|---:|---:|---:|---:|---|---:|---|")
 for path in sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", "models", "bayesnets", "*.uai"))):
     cards, scopes, _ = parse_uai(open(path).read())
@@ -50,8 +50,9 @@ for path in sorted(glob.glob(os.path.join(ROOT, "oracle", "_ref", "models", "bay
     built = "-"
     if not lanes:
         q = DryPlan(cards, scopes, [], order)
-        segs = q.segments(0)           # what the (experimental) segment builder makes of it, small steps first
-        built = "%d (%d segments)" % (q.n_steps() - sum(e - a for a, e, *_ in segs) + len(segs), len(segs))
+        segs = q.segments(0)           # K10: tasks (subtrees of small steps) grouped by dependency level
+        launches, groups, levels = q.launches()
+        built = "%d (%d tasks in %d group launches, %d levels)" % (launches, len(segs), groups, levels)
         q.close()
     print("| %s | %d | %d | %.2f | %.2f | %d | %d | %.1f %% | %s | %d | %s |"
           % (os.path.basename(path)[:-4], n, width, (t1 - t0) * 1e3, (t2 - t1b) * 1e3, ns, sum(small),

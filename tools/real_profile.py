@@ -18,7 +18,15 @@ for name in sys.argv[1:] or ["Munin1"]:
     z, ms = bn.partition({}, "mf")
     bn.drop_plans()
     z, ms = bn.partition({}, "mf")
-    print(name, "Z", z, "e2e %.2f ms" % ms, bn.last_timing)
+    reps = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        z2, _ = bn.partition({}, "mf")
+        reps.append((time.perf_counter() - t0) * 1e3)
+    assert z2 == z
+    launches0 = ctx.launches
+    bn.partition({}, "mf")
+    print(name, "Z", z, "e2e %.2f ms" % ms, bn.last_timing, "replay %.3f ms (min of 5), %d launches per query" % (min(reps), ctx.launches - launches0))
     order, width = bn.order(list(range(bn.nvars)), {}, "mf")
     plan = bn.plan([], order)
     res = torch.zeros(2, dtype=torch.float64, device="cuda")
