@@ -16,9 +16,14 @@
 // bucket then has the eliminated variable as its fastest axis (32-byte loads) and
 // scopes are mutually order-compatible (pure broadcasts, no transposes).
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <thread>
 #include <vector>
 
 #include "batched.hpp"
@@ -143,7 +148,7 @@ struct bnpp_ve_plan {
     uint64_t union_entries = 0, bytes = 0, peak_bytes = 0, max_step_entries = 0;
     // replay state: one resolved launch per step and a fixed arena for the intermediates, so a
     // run is pointer patching + cudaLaunchKernel (the host must not be what small steps wait for)
-    std::vector<bnpp::LaunchDesc> exec;
+    std::vector<std::unique_ptr<bnpp::LaunchDesc>> exec;     // resolved lazily: only the steps that run as their own launch
     std::vector<char> exec_planned;
     std::vector<uint64_t> arena_off;        // per PlanFactor, in doubles
     uint64_t arena_doubles = 0;
@@ -463,7 +468,8 @@ bool plan_step(bnpp_ve_plan *pl, size_t s)
         dst = arena_standin + pl->arena_off[st.out];
     }
     pl->exec_planned[s] = 1;
-    return contract_plan(pl->ctx, (int)st.operands.size(), ops, &os, st.elim, 0, dst, nullptr, &pl->exec[s]) == BNPP_OK;
+    if (!pl->exec[s]) pl->exec[s].reset(new LaunchDesc());
+    return contract_plan(pl->ctx, (int)st.operands.size(), ops, &os, st.elim, 0, dst, nullptr, pl->exec[s].get()) == BNPP_OK;
 }
 
 
@@ -928,44 +934,73 @@ void build_segments(bnpp_ve_plan *pl)
     const size_t ns = pl->steps.size();
     pl->group_at.assign(ns, -1);
     if (!pl->levels_built || pl->step_task.size() != ns) return;
-    size_t s = 0;
-    while (s < ns) {
-        if (pl->step_task[s] < 0) { ++s; continue; }
-        // the small steps of one level are contiguous: [s, e)
-        size_t e = s;
-        while (e < ns && pl->step_task[e] >= 0 && pl->step_level[e] == pl->step_level[s]) ++e;
+    // tasks = maximal runs of steps with the same task root; groups = maximal runs of tasks with the same level
+    std::vector<bnpp_ve_plan::Segment> all;
+    for (size_t t = 0; t < ns;) {
+        if (pl->step_task[t] < 0) { ++t; continue; }
+        size_t u = t;
+        while (u < ns && pl->step_task[u] == pl->step_task[t]) ++u;
+        bnpp_ve_plan::Segment seg;
+        seg.a = (int)t;
+        seg.b = (int)u;
+        seg.level = pl->step_level[t];
+        all.push_back(std::move(seg));
+        t = u;
+    }
+    // the programs are independent of one another: encode them on a few host threads (the offset tables of a
+    // 1000-bucket network are ~0.5 M words; a one-shot CLI query pays for them inside its timed region)
+    auto encode = [&](size_t i) {
+        std::vector<int> order;
+        for (int k = all[i].a; k < all[i].b; ++k) order.push_back(k);
+        fused_encode(pl, order, true, all[i].prog);
+    };
+    const auto tb0 = std::chrono::steady_clock::now();
+    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    if (all.size() >= 8 && hw > 1) {
+        std::atomic<size_t> next(0);
+        std::vector<std::thread> pool;
+        for (unsigned w = 0; w < hw; ++w)
+            pool.emplace_back([&] {
+                for (size_t i = next.fetch_add(1); i < all.size(); i = next.fetch_add(1)) encode(i);
+            });
+        for (auto &th : pool) th.join();
+    } else {
+        for (size_t i = 0; i < all.size(); ++i) encode(i);
+    }
+    const auto tb1 = std::chrono::steady_clock::now();
+    if (getenv("BNPP_TIMING"))
+        fprintf(stderr, "bnpp timing: %zu task programs encoded in %.3f ms on %u thread(s)\n", all.size(),
+                std::chrono::duration<double, std::milli>(tb1 - tb0).count(), all.size() >= 8 ? hw : 1u);
+    for (size_t i = 0; i < all.size();) {
+        size_t j = i;
+        while (j < all.size() && all[j].level == all[i].level && all[j].a == (j == i ? all[i].a : all[j - 1].b)) ++j;
         bnpp_ve_plan::Group g;
-        g.a = (int)s;
-        g.b = (int)e;
+        g.a = all[i].a;
+        g.b = all[j - 1].b;
         g.first_seg = (int)pl->segs.size();
         bool ok = true;
-        for (size_t t = s; t < e && ok;) {
-            size_t u = t;
-            while (u < e && pl->step_task[u] == pl->step_task[t]) ++u;
-            bnpp_ve_plan::Segment seg;
-            seg.a = (int)t;
-            seg.b = (int)u;
-            seg.level = pl->step_level[t];
-            std::vector<int> order;
-            for (size_t i = t; i < u; ++i) order.push_back((int)i);
-            fused_encode(pl, order, true, seg.prog);
-            ok = seg.prog.ok && fused_smem_bytes(128, seg.prog.arena) <= kFusedSmemLimit;
-            if (ok) {
-                g.max_arena = std::max(g.max_arena, seg.prog.arena);
-                pl->segs.push_back(std::move(seg));
+        for (size_t t = i; t < j && ok; ++t) ok = all[t].prog.ok && fused_smem_bytes(128, all[t].prog.arena) <= kFusedSmemLimit;
+        if (ok) {
+            for (size_t t = i; t < j; ++t) {
+                g.max_arena = std::max(g.max_arena, all[t].prog.arena);
+                pl->segs.push_back(std::move(all[t]));
             }
-            t = u;
-        }
-        if (!ok) {
-            pl->segs.resize(g.first_seg);       // this level's small steps stay one launch each
-        } else {
-            g.n_segs = (int)pl->segs.size() - g.first_seg;
-            pl->group_at[s] = (int)pl->groups.size();
+            g.n_segs = (int)(j - i);
+            pl->group_at[g.a] = (int)pl->groups.size();
             pl->groups.push_back(g);
-        }
-        s = e;
+        }       // else: this level's small steps stay one launch each
+        i = j;
     }
+    const auto tb2 = std::chrono::steady_clock::now();
     // one buffer for all programs, one for all offset tables, one record per task
+    size_t prog_words = 0, tab_words = 0;
+    for (const auto &seg : pl->segs) {
+        prog_words += seg.prog.prog.size();
+        tab_words += seg.prog.offtab.size() + 4;
+    }
+    pl->tasks_prog.reserve(prog_words);
+    pl->tasks_tab.reserve(tab_words);
+    pl->tasks_rec.reserve(pl->segs.size());
     for (const auto &seg : pl->segs) {
         TaskRecord r;
         r.prog_off = (uint32_t)pl->tasks_prog.size();
@@ -979,6 +1014,9 @@ void build_segments(bnpp_ve_plan *pl)
         while (pl->tasks_tab.size() % 4) pl->tasks_tab.push_back(0);
         pl->tasks_rec.push_back(r);
     }
+    if (getenv("BNPP_TIMING"))
+        fprintf(stderr, "bnpp timing: groups %.3f ms, one buffer %.3f ms\n", std::chrono::duration<double, std::milli>(tb2 - tb1).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tb2).count());
 }
 
 // device copies of the task programs; addresses inside them (CPT tables, arena slots) patched when they moved
@@ -1326,10 +1364,11 @@ int bnpp_ve_plan_destroy(bnpp_ve_plan *pl)
     if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
     if (pl->graph) cudaGraphDestroy(pl->graph);
     if (pl->arena) bnpp_free(pl->ctx, pl->arena);
-    for (LaunchDesc &d : pl->exec) contract_release(pl->ctx, d);
-    if (pl->ctx && pl->ctx->last_desc && !pl->exec.empty() && pl->ctx->last_desc >= (void *)&pl->exec.front() &&
-        pl->ctx->last_desc <= (void *)&pl->exec.back())
-        pl->ctx->last_desc = nullptr;       // bnpp_last_launch must not follow a pointer into a dead plan
+    for (auto &d : pl->exec)
+        if (d) {
+            contract_release(pl->ctx, *d);
+            if (pl->ctx && pl->ctx->last_desc == d.get()) pl->ctx->last_desc = nullptr;      // bnpp_last_launch must not follow a pointer into a dead plan
+        }
     free_tasks(pl);
     if (pl->fused.prog_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.prog_dev));
     if (pl->fused.offtab_dev) bnpp_free(pl->ctx, reinterpret_cast<double *>(pl->fused.offtab_dev));
@@ -1648,6 +1687,7 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
 {
     if (!pl || !pl->ctx || !result_dev) return BNPP_EINVAL;
     bnpp_ctx *ctx = pl->ctx;
+    const auto t_run0 = std::chrono::steady_clock::now();
     if (pl->n_obs && !obs_val) return fail(ctx, BNPP_EINVAL, "VE plan: evidence values missing");
     for (int i = 0; i < pl->n_obs; ++i)
         if (pl->obs_card[i] && obs_val[i] >= pl->obs_card[i])
@@ -1673,6 +1713,9 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
     bool ev_inline = pl->n_obs <= kFusedInlineEv;      // the evidence values travel in the kernel parameters as bytes
     for (int i = 0; i < pl->n_obs && ev_inline; ++i) ev_inline = obs_val[i] <= 255;
     if (ev_inline) fused_g = fused_pick(pl, 1);
+    if (getenv("BNPP_TIMING") && pl->runs == 0)
+        fprintf(stderr, "bnpp timing: up to the choice of the path %.3f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count());
     if (fused_g) {
         // K9: every step is small -- the whole plan is one launch, intermediates in shared memory
         rc = run_fused(pl, fused_g, tables_dev, 1, nullptr, obs_val, result_dev, z_dev);
@@ -1680,23 +1723,36 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
         rc = run_dynamic(pl, ptr, result_dev, z_dev);
     } else {
         if (!pl->arena && pl->arena_doubles) {
+            const auto t_a0 = std::chrono::steady_clock::now();
             rc = bnpp_alloc(ctx, pl->arena_doubles, &pl->arena);
             if (rc != BNPP_OK) return rc;
+            if (getenv("BNPP_TIMING"))
+                fprintf(stderr, "bnpp timing: arena of %.1f MB allocated in %.3f ms\n", pl->arena_doubles * 8e-6,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a0).count());
         }
         if (pl->exec.size() != pl->steps.size()) {
-            pl->exec.assign(pl->steps.size(), LaunchDesc());
+            pl->exec.clear();
+            pl->exec.resize(pl->steps.size());
             pl->exec_planned.assign(pl->steps.size(), 0);
         }
         for (size_t i = 0; i < pl->f.size(); ++i)
             if (pl->f[i].src < 0) ptr[i] = pl->arena + pl->arena_off[i];
         // K10: the small tasks of every dependency level as ONE ve_tasks launch (a node of the replay graph like any other)
         const bool seg_on = pl->segments_mode && pl->levels_built && ev_inline && !pl->profiling;
+        static const bool timing = getenv("BNPP_TIMING") != nullptr;
+        const auto t_0 = std::chrono::steady_clock::now();
         if (seg_on && !pl->segments_built) build_segments(pl);
+        const auto t_1 = std::chrono::steady_clock::now();
         const bool use_groups = seg_on && !pl->groups.empty();
         if (use_groups) {
             rc = upload_tasks(pl, tables_dev);
             if (rc != BNPP_OK) return rc;
         }
+        const auto t_2 = std::chrono::steady_clock::now();
+        if (timing && pl->runs == 0)
+            fprintf(stderr, "bnpp timing: build_segments %.3f ms, upload_tasks %.3f ms (%zu tasks, %zu groups, prog %zu words, tables %zu words)\n",
+                    std::chrono::duration<double, std::milli>(t_1 - t_0).count(), std::chrono::duration<double, std::milli>(t_2 - t_1).count(),
+                    pl->segs.size(), pl->groups.size(), pl->tasks_prog.size(), pl->tasks_tab.size());
         const bool graphed = pl->use_graph && !pl->profiling && pl->steps.size() > 1 && pl->runs >= 1 &&
                              (!pl->graph_exec || pl->graph_groups == use_groups);
         bool fresh = false;
@@ -1708,6 +1764,7 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
         }
         cudaGraphNode_t prev = nullptr;
         uint64_t n_launched = 0;
+        double t_plan_steps = 0.0;
         for (size_t s = 0; s < pl->steps.size() && rc == BNPP_OK; ++s) {
             if (use_groups && pl->group_at[s] >= 0) {
                 bnpp_ve_plan::Group &g = pl->groups[pl->group_at[s]];
@@ -1745,13 +1802,17 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             for (size_t q = 0; q < st.operands.size(); ++q) in[q] = ptr[st.operands[q]];
             double *dst = st.out == -2 ? result_dev + st.roff : pl->arena + pl->arena_off[st.out];
             double *z = (st.out == -2 && st.want_z) ? z_dev : nullptr;
-            if (!pl->exec_planned[s] && !plan_step(pl, s)) return fail(ctx, BNPP_EINVAL, "VE plan: a step could not be resolved");
+            if (!pl->exec_planned[s]) {
+                const auto t_p0 = std::chrono::steady_clock::now();
+                if (!plan_step(pl, s)) return fail(ctx, BNPP_EINVAL, "VE plan: a step could not be resolved");
+                t_plan_steps += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_p0).count();
+            }
             ++n_launched;
             if (!(graphed && pl->use_graph)) {
-                rc = contract_launch(ctx, pl->exec[s], in, dst, z);
+                rc = contract_launch(ctx, *pl->exec[s], in, dst, z);
                 continue;
             }
-            LaunchDesc &d = pl->exec[s];
+            LaunchDesc &d = *pl->exec[s];
             ParamsHead &h = d.head();
             bool moved = fresh || h.out != dst || h.z != z;
             for (size_t q = 0; q < st.operands.size(); ++q) moved = moved || h.in[q] != in[q];
@@ -1774,6 +1835,10 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
             if (e != cudaSuccess) return cuda_fail(ctx, e, "CUDA graph node");
             if (fresh) prev = pl->nodes[s];
         }
+        if (timing && pl->runs == 0)
+            fprintf(stderr, "bnpp timing: resolving the wide steps' launches (contract_plan) %.3f ms, %llu launches, launch loop %.3f ms\n",
+                    t_plan_steps, (unsigned long long)n_launched,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_2).count());
         if (graphed && pl->use_graph && rc == BNPP_OK) {
             if (fresh) BNPP_CUDA(ctx, cudaGraphInstantiate(&pl->graph_exec, pl->graph, 0));
             BNPP_CUDA(ctx, cudaGraphLaunch(pl->graph_exec, ctx->stream));
@@ -1783,12 +1848,15 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
         }
         if (pl->profiling) {
             pl->step_kernel.resize(pl->steps.size());
-            for (size_t s = 0; s < pl->steps.size(); ++s) pl->step_kernel[s] = pl->exec[s].name();
+            for (size_t s = 0; s < pl->steps.size(); ++s) pl->step_kernel[s] = pl->exec[s] ? pl->exec[s]->name() : std::string();
         }
     }
     if (rc == BNPP_OK && pl->is_mar && pl->normalize)
         rc = normalize_segments(ctx, result_dev, pl->mar_off_dev, pl->mar_size_dev, (int)pl->mar_off.size());
     if (pl->profiling) cudaEventRecord(pl->ev[pl->steps.size()], ctx->stream);
+    if (getenv("BNPP_TIMING") && pl->runs == 0)
+        fprintf(stderr, "bnpp timing: first run of the plan enqueued in %.3f ms (host)\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_run0).count());
     pl->runs++;
     return rc;
 }

