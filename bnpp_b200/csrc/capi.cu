@@ -20,6 +20,25 @@ int fail(bnpp_ctx *ctx, int code, const std::string &msg)
     return code;
 }
 
+int stage_upload(bnpp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes)
+{
+    if (!bytes) return BNPP_OK;
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (!ctx->stage || need > ctx->stage_bytes) {
+        // no ring, or a table larger than the ring: the (synchronising) copy from pageable memory
+        BNPP_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return BNPP_OK;
+    }
+    if (ctx->stage_off + need > ctx->stage_bytes) {
+        BNPP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // every earlier copy out of the ring is done: wrap around
+        ctx->stage_off = 0;
+    }
+    memcpy(ctx->stage + ctx->stage_off, src_host, bytes);
+    BNPP_CUDA(ctx, cudaMemcpyAsync(dst_dev, ctx->stage + ctx->stage_off, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stage_off += need;
+    return BNPP_OK;
+}
+
 int cuda_fail(bnpp_ctx *ctx, cudaError_t e, const char *what)
 {
     if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);
@@ -65,6 +84,12 @@ int bnpp_ctx_create(int device, void *stream, bnpp_ctx **out)
     BNPP_CUDA(ctx, cudaMalloc(&ctx->ticket, 64));
     BNPP_CUDA(ctx, cudaMemset(ctx->ticket, 0, 64));
     ctx->status = ctx->ticket + 4;
+    ctx->stage_bytes = 4u << 20;
+    if (cudaHostAlloc(reinterpret_cast<void **>(&ctx->stage), ctx->stage_bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->stage = nullptr;
+        ctx->stage_bytes = 0;
+    }
     *out = ctx;
     return BNPP_OK;
 }
@@ -76,6 +101,7 @@ int bnpp_ctx_destroy(bnpp_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->partials);
     cudaFree(ctx->ticket);
+    if (ctx->stage) cudaFreeHost(ctx->stage);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return BNPP_OK;

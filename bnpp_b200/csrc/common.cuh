@@ -116,10 +116,16 @@ struct bnpp_ctx {
     std::string last_error;
     std::string last_kernel;
     void *last_desc = nullptr;         // bnpp::LaunchDesc of the most recent contraction (name formatted on demand)
+    // pinned staging ring for the small tables a plan uploads while it resolves its launches (offset tables of the
+    // multi-valued kernels, task programs): a copy from pageable memory would synchronise the stream every time
+    unsigned char *stage = nullptr;
+    size_t stage_bytes = 0, stage_off = 0;
     uint32_t last_grid = 0, last_block = 0;
 };
 
 namespace bnpp {
+// host -> device copy of a small table, stream-ordered and asynchronous (through the context's pinned ring)
+int stage_upload(bnpp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int fail(bnpp_ctx *ctx, int code, const std::string &msg);
 int cuda_fail(bnpp_ctx *ctx, cudaError_t e, const char *what);
 #define BNPP_CUDA(ctx, expr)                                                   \

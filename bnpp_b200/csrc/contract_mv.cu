@@ -223,6 +223,7 @@ static int mv_resident(bnpp_ctx *ctx, mv_fn fn, unsigned smem)
     static std::map<std::pair<int, const void *>, unsigned> granted;
     std::lock_guard<std::mutex> lock(mu);
     const auto key = std::make_pair(ctx->device, reinterpret_cast<const void *>(fn));
+    smem = ((smem + 1023u) >> 10) << 10;        // opt-in and occupancy are asked per KB of shared memory (cached)
     auto it = granted.find(key);
     if (it == granted.end() || it->second < smem) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -231,11 +232,16 @@ static int mv_resident(bnpp_ctx *ctx, mv_fn fn, unsigned smem)
         }
         granted[key] = smem;
     }
+    static std::map<std::pair<std::pair<int, const void *>, unsigned>, int> occupancy;       // (device, fn, KB of shared memory)
+    const auto okey = std::make_pair(key, smem >> 10);
+    auto oc = occupancy.find(okey);
+    if (oc != occupancy.end()) return oc->second;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
+    occupancy[okey] = per_sm;
     return per_sm;
 }
 
@@ -377,11 +383,10 @@ int plan_mv(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *sx
     double *store = nullptr;
     int rc = bnpp_alloc(ctx, words / 2 + 2, &store);
     if (rc != BNPP_OK) return rc;
-    // stream-ordered; the pageable source is staged before the call returns
-    cudaError_t ce = cudaMemcpyAsync(store, tab.data(), words * 4, cudaMemcpyHostToDevice, ctx->stream);
-    if (ce != cudaSuccess) {
+    rc = stage_upload(ctx, store, tab.data(), words * 4);
+    if (rc != BNPP_OK) {
         bnpp_free(ctx, store);
-        return cuda_fail(ctx, ce, "contract_mv table upload");
+        return rc;
     }
     d->mv_tab = reinterpret_cast<uint32_t *>(store);
     p.tab = d->mv_tab;

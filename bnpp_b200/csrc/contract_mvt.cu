@@ -208,6 +208,7 @@ int mvt_resident(bnpp_ctx *ctx, mvt_fn fn, unsigned smem)
     static std::map<std::pair<int, const void *>, unsigned> granted;
     std::lock_guard<std::mutex> lock(mu);
     const auto key = std::make_pair(ctx->device, reinterpret_cast<const void *>(fn));
+    smem = ((smem + 1023u) >> 10) << 10;        // opt-in and occupancy are asked per KB of shared memory (cached)
     auto it = granted.find(key);
     if (it == granted.end() || it->second < smem) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
@@ -216,11 +217,16 @@ int mvt_resident(bnpp_ctx *ctx, mvt_fn fn, unsigned smem)
         }
         granted[key] = smem;
     }
+    static std::map<std::pair<std::pair<int, const void *>, unsigned>, int> occupancy;       // (device, fn, KB of shared memory)
+    const auto okey = std::make_pair(key, smem >> 10);
+    auto oc = occupancy.find(okey);
+    if (oc != occupancy.end()) return oc->second;
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
+    occupancy[okey] = per_sm;
     return per_sm;
 }
 
@@ -389,10 +395,10 @@ int plan_mvt(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *s
     double *store = nullptr;
     int rc = bnpp_alloc(ctx, tab.size() / 2 + 2, &store);
     if (rc != BNPP_OK) return rc;
-    cudaError_t ce = cudaMemcpyAsync(store, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, ctx->stream);
-    if (ce != cudaSuccess) {
+    rc = stage_upload(ctx, store, tab.data(), tab.size() * 4);
+    if (rc != BNPP_OK) {
         bnpp_free(ctx, store);
-        return cuda_fail(ctx, ce, "contract_mvt table upload");
+        return rc;
     }
     d->mv_tab = reinterpret_cast<uint32_t *>(store);
     p.rowtab = d->mv_tab;

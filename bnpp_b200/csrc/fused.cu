@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kFusedThreads) ve_tasks(const __grid_constant_
     }
 }
 
-bool fused_valid_g(int G) { return G == 8 || G == 16 || G == 32 || G == 128; }
+bool fused_valid_g(int G) { return G == 2 || G == 4 || G == 8 || G == 16 || G == 32 || G == 128; }
 
 size_t fused_smem_bytes(int G, uint32_t arena)
 {
@@ -313,6 +313,8 @@ int fused_launch(bnpp_ctx *ctx, int G, const FusedLaunch &p)
 {
     fused_fn fn = nullptr;
     switch (G) {
+    case 2: fn = ve_fused<2>; break;
+    case 4: fn = ve_fused<4>; break;
     case 8: fn = ve_fused<8>; break;
     case 16: fn = ve_fused<16>; break;
     case 32: fn = ve_fused<32>; break;
@@ -342,7 +344,7 @@ int fused_launch(bnpp_ctx *ctx, int G, const FusedLaunch &p)
                                     ctx->stream));
     ctx->launches++;
     ctx->last_desc = nullptr;
-    ctx->last_kernel = G == 8 ? "ve_fused<G=8>" : (G == 16 ? "ve_fused<G=16>" : (G == 32 ? "ve_fused<G=32>" : "ve_fused<G=128>"));
+    ctx->last_kernel = G == 2 ? "ve_fused<G=2>" : G == 4 ? "ve_fused<G=4>" : G == 8 ? "ve_fused<G=8>" : (G == 16 ? "ve_fused<G=16>" : (G == 32 ? "ve_fused<G=32>" : "ve_fused<G=128>"));
     ctx->last_grid = (uint32_t)blocks;
     ctx->last_block = kFusedThreads;
     return BNPP_OK;

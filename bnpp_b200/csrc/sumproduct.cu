@@ -46,6 +46,15 @@ struct bnpp_fg {
     // per message entry: every Ising / pairwise factor), a warp per edge otherwise
     int n_small = 0, n_big = 0;
     int32_t *small_edges = nullptr, *big_edges = nullptr;
+    // pre-resolved reads of every message update (built once, host side): what a sweep costs is the LATENCY of a chain of
+    // dependent loads, so each update gets everything it needs from one record -- no CSR walk, no div/mod per term
+    //   variable -> factor : a_hdr[e] = (first word in a_nb, count | card << 16); a_nb = message offsets of the variable's OTHER edges
+    //   factor -> variable (small factors): b_hdr[e] = (r | sub << 8 | w << 16, first word in b_terms, table offset lo, hi);
+    //       b_terms = for i < r, ts < sub: table index, then the message entry of each other slot (w - 1 words)
+    uint2 *a_hdr = nullptr;
+    uint32_t *a_nb = nullptr;
+    uint4 *b_hdr = nullptr;
+    uint32_t *b_terms = nullptr;
 };
 
 namespace bnpp {
@@ -69,11 +78,22 @@ __device__ __forceinline__ void note_error(unsigned long long *maxerr, double er
     if (err > 0.0) atomicMax(maxerr, (unsigned long long)__double_as_longlong(err));
 }
 
+// one atomic per warp instead of one per message: the max-error word is a single L2 address, and 15 680 atomics on
+// it per phase (a 40x40 Ising grid) cost more than the phase itself
+__device__ __forceinline__ void note_error_warp(unsigned long long *maxerr, double worst)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, worst, o);
+        if (other > worst) worst = other;
+    }
+    if ((threadIdx.x & 31) == 0) note_error(maxerr, worst);
+}
+
 // variable -> factor, code/graph.cpp:334-362: m_{v->f} = normalize(prod_{g in N(v)\f} m_{g->v})
-__device__ __forceinline__ void var_to_fac_edge(int e, const uint32_t *__restrict__ evar, const uint32_t *__restrict__ card,
+__device__ __forceinline__ double var_to_fac_edge(int e, const uint32_t *__restrict__ evar, const uint32_t *__restrict__ card,
                                                 const uint32_t *__restrict__ moff, const int32_t *__restrict__ voff,
-                                                const int32_t *__restrict__ vedges, const double *f2v, double *v2f,
-                                                unsigned long long *maxerr)
+                                                const int32_t *__restrict__ vedges, const double *f2v, double *v2f)
 {
     const uint32_t v = evar[e], r = card[v];
     const int b = voff[v], n = voff[v + 1];
@@ -99,30 +119,160 @@ __device__ __forceinline__ void var_to_fac_edge(int e, const uint32_t *__restric
         if (err > worst) worst = err;
         v2f[moff[e] + i] = nv;
     }
-    note_error(maxerr, worst);
+    return worst;
 }
 
-__global__ void __launch_bounds__(128) fg_var_to_fac_kernel(int nedges, const uint32_t *__restrict__ evar,
-                                                            const uint32_t *__restrict__ card,
+constexpr int kMaxNb = 8;       // neighbours / terms kept in registers by the record-driven updates
+
+// variable -> factor from the edge's record: all neighbour messages are requested before the first multiply
+__device__ __forceinline__ double var_to_fac_rec(int e, const uint2 *__restrict__ a_hdr, const uint32_t *__restrict__ a_nb,
+                                                 const uint32_t *__restrict__ moff, const double *f2v, double *v2f)
+{
+    const uint2 h = __ldg(a_hdr + e);
+    const uint32_t n = h.y & 0xffffu, r = h.y >> 16, mo = __ldg(moff + e);
+    if (r == 2 && n <= (uint32_t)kMaxNb) {
+        uint32_t nb[kMaxNb];
+#pragma unroll
+        for (int q = 0; q < kMaxNb; ++q) nb[q] = q < (int)n ? __ldg(a_nb + h.x + q) : 0u;
+        double m0[kMaxNb], m1[kMaxNb];
+#pragma unroll
+        for (int q = 0; q < kMaxNb; ++q)
+            if (q < (int)n) {
+                m0[q] = __ldcg(f2v + nb[q]);
+                m1[q] = __ldcg(f2v + nb[q] + 1);
+            }
+        const double o0 = __ldcg(v2f + mo), o1 = __ldcg(v2f + mo + 1);
+        double p0 = 1.0, p1 = 1.0;
+#pragma unroll
+        for (int q = 0; q < kMaxNb; ++q)
+            if (q < (int)n) {
+                p0 *= m0[q];
+                p1 *= m1[q];
+            }
+        double z = 0.0;
+        z += p0;
+        z += p1;
+        const double n0 = p0 / z, n1 = p1 / z;
+        double worst = 0.0;
+        const double e0 = fabs(o0 - n0) / o0, e1 = fabs(o1 - n1) / o1;
+        if (e0 > worst) worst = e0;
+        if (e1 > worst) worst = e1;
+        v2f[mo] = n0;
+        v2f[mo + 1] = n1;
+        return worst;
+    }
+    // any cardinality / degree: two passes over the neighbour list
+    double z = 0.0;
+    for (uint32_t i = 0; i < r; ++i) {
+        double p = 1.0;
+        for (uint32_t q = 0; q < n; ++q) p *= __ldcg(f2v + __ldg(a_nb + h.x + q) + i);
+        z += p;
+    }
+    double worst = 0.0;
+    for (uint32_t i = 0; i < r; ++i) {
+        double p = 1.0;
+        for (uint32_t q = 0; q < n; ++q) p *= __ldcg(f2v + __ldg(a_nb + h.x + q) + i);
+        const double nv = p / z;
+        const double ov = __ldcg(v2f + mo + i);
+        const double err = fabs(ov - nv) / ov;
+        if (err > worst) worst = err;
+        v2f[mo + i] = nv;
+    }
+    return worst;
+}
+
+// factor -> variable for a small factor from the edge's record
+__device__ __forceinline__ double fac_to_var_rec(int e, const uint4 *__restrict__ b_hdr, const uint32_t *__restrict__ b_terms,
+                                                 const uint32_t *__restrict__ moff, const double *__restrict__ ftab, const double *v2f,
+                                                 double *f2v, double *tmp)
+{
+    const uint4 h = __ldg(b_hdr + e);
+    const uint32_t r = h.x & 0xffu, sub = (h.x >> 8) & 0xffu, w = h.x >> 16, mo = __ldg(moff + e);
+    const double *tab = ftab + (((uint64_t)h.w << 32) | h.z);
+    const uint32_t *t = b_terms + h.y;
+    if (r == 2 && w <= 2 && sub <= 2) {
+        // the pairwise / unary case (every factor of an Ising grid): at most 4 terms of at most 2 factors each
+        uint32_t words[8];
+        const uint32_t nw = 2u * sub * w;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) words[q] = q < (int)nw ? __ldg(t + q) : 0u;
+        double val[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            if (q < (int)nw) val[q] = ((uint32_t)q % w == 0) ? __ldg(tab + words[q]) : __ldcg(v2f + words[q]);
+        const double o0 = __ldcg(f2v + mo), o1 = __ldcg(f2v + mo + 1);
+        double part[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int ts = 0; ts < 2; ++ts)
+                if (ts < (int)sub) {
+                    const int q = (i * (int)sub + ts) * (int)w;
+                    double p = val[q];
+                    if (w == 2) p *= val[q + 1];
+                    acc += p;
+                }
+            part[i] = acc;
+        }
+        double z = 0.0;
+        z += part[0];
+        z += part[1];
+        const double n0 = part[0] / z, n1 = part[1] / z;
+        double worst = 0.0;
+        const double e0 = fabs(o0 - n0) / o0, e1 = fabs(o1 - n1) / o1;
+        if (e0 > worst) worst = e0;
+        if (e1 > worst) worst = e1;
+        f2v[mo] = n0;
+        f2v[mo + 1] = n1;
+        return worst;
+    }
+    double z = 0.0;
+    for (uint32_t i = 0; i < r; ++i) {
+        double part = 0.0;
+        for (uint32_t ts = 0; ts < sub; ++ts) {
+            const uint32_t *rec = t + (i * sub + ts) * w;
+            double p = __ldg(tab + __ldg(rec));
+            for (uint32_t u = 1; u < w; ++u) p *= __ldcg(v2f + __ldg(rec + u));
+            part += p;
+        }
+        tmp[mo + i] = part;
+        z += part;
+    }
+    double worst = 0.0;
+    for (uint32_t i = 0; i < r; ++i) {
+        const double nv = tmp[mo + i] / z;
+        const double ov = __ldcg(f2v + mo + i);
+        const double err = fabs(ov - nv) / ov;
+        if (err > worst) worst = err;
+        f2v[mo + i] = nv;
+    }
+    return worst;
+}
+
+__global__ void __launch_bounds__(128) fg_var_to_fac_kernel(int nedges, const uint2 *__restrict__ a_hdr,
+                                                            const uint32_t *__restrict__ a_nb,
                                                             const uint32_t *__restrict__ moff,
-                                                            const int32_t *__restrict__ voff,
-                                                            const int32_t *__restrict__ vedges,
                                                             const double *__restrict__ f2v, double *__restrict__ v2f,
                                                             unsigned long long *maxerr)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nedges) return;
-    var_to_fac_edge(e, evar, card, moff, voff, vedges, f2v, v2f, maxerr);
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    double worst = 0.0;
+    for (int e = gtid; e < nedges; e += gthreads) {
+        const double w_ = var_to_fac_rec(e, a_hdr, a_nb, moff, f2v, v2f);
+        if (w_ > worst) worst = w_;
+    }
+    note_error_warp(maxerr, worst);
 }
 
 // factor -> variable, code/graph.cpp:364-391: one warp per edge (f, slot j):
 // m_{f->v}[i] = sum over the factor entries with digit_j = i of  F * prod_{u != j} m_{u->f}
-__device__ __forceinline__ void fac_to_var_edge(int e, int lane, const int32_t *__restrict__ efac,
+__device__ __forceinline__ double fac_to_var_edge(int e, int lane, const int32_t *__restrict__ efac,
                                                 const uint32_t *__restrict__ evar, const int32_t *__restrict__ foff,
                                                 const uint32_t *__restrict__ card, const uint32_t *__restrict__ moff,
                                                 const uint64_t *__restrict__ toff, const uint32_t *__restrict__ estride,
                                                 const uint32_t *__restrict__ fsize, const double *__restrict__ ftab,
-                                                const double *v2f, double *f2v, double *tmp, unsigned long long *maxerr)
+                                                const double *v2f, double *f2v, double *tmp)
 {
     const int f = efac[e];
     const int e0 = foff[f], w = foff[f + 1] - e0;
@@ -161,18 +311,17 @@ __device__ __forceinline__ void fac_to_var_edge(int e, int lane, const int32_t *
         const double other = __shfl_down_sync(0xffffffffu, worst, o);
         if (other > worst) worst = other;
     }
-    if (lane == 0) note_error(maxerr, worst);
+    return worst;       // lane 0 holds the message's worst relative change
 }
 
 constexpr uint32_t kSmallSub = 8;
 
 // the same update by ONE thread (small factors: a warp per edge would leave 30 lanes idle)
-__device__ __forceinline__ void fac_to_var_edge_small(int e, const int32_t *__restrict__ efac, const uint32_t *__restrict__ evar,
+__device__ __forceinline__ double fac_to_var_edge_small(int e, const int32_t *__restrict__ efac, const uint32_t *__restrict__ evar,
                                                       const int32_t *__restrict__ foff, const uint32_t *__restrict__ card,
                                                       const uint32_t *__restrict__ moff, const uint64_t *__restrict__ toff,
                                                       const uint32_t *__restrict__ estride, const uint32_t *__restrict__ fsize,
-                                                      const double *__restrict__ ftab, const double *v2f, double *f2v, double *tmp,
-                                                      unsigned long long *maxerr)
+                                                      const double *__restrict__ ftab, const double *v2f, double *f2v, double *tmp)
 {
     const int f = efac[e];
     const int e0 = foff[f], w = foff[f + 1] - e0;
@@ -204,11 +353,12 @@ __device__ __forceinline__ void fac_to_var_edge_small(int e, const int32_t *__re
         if (err > worst) worst = err;
         f2v[moff[e] + i] = nv;
     }
-    note_error(maxerr, worst);
+    return worst;
 }
 
 __global__ void __launch_bounds__(128) fg_fac_to_var_kernel(int n_small, const int32_t *__restrict__ small_edges, int n_big,
                                                             const int32_t *__restrict__ big_edges,
+                                                            const uint4 *__restrict__ b_hdr, const uint32_t *__restrict__ b_terms,
                                                             const int32_t *__restrict__ efac,
                                                             const uint32_t *__restrict__ evar,
                                                             const int32_t *__restrict__ foff,
@@ -222,11 +372,17 @@ __global__ void __launch_bounds__(128) fg_fac_to_var_kernel(int n_small, const i
                                                             double *__restrict__ tmp, unsigned long long *maxerr)
 {
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-    for (int i = gtid; i < n_small; i += gthreads)
-        fac_to_var_edge_small(small_edges[i], efac, evar, foff, card, moff, toff, estride, fsize, ftab, v2f, f2v, tmp, maxerr);
+    double worst = 0.0;
+    for (int i = gtid; i < n_small; i += gthreads) {
+        const double w_ = fac_to_var_rec(small_edges[i], b_hdr, b_terms, moff, ftab, v2f, f2v, tmp);
+        if (w_ > worst) worst = w_;
+    }
     const int lane = threadIdx.x & 31;
-    for (int i = gtid >> 5; i < n_big; i += gthreads >> 5)
-        fac_to_var_edge(big_edges[i], lane, efac, evar, foff, card, moff, toff, estride, fsize, ftab, v2f, f2v, tmp, maxerr);
+    for (int i = gtid >> 5; i < n_big; i += gthreads >> 5) {
+        const double w_ = fac_to_var_edge(big_edges[i], lane, efac, evar, foff, card, moff, toff, estride, fsize, ftab, v2f, f2v, tmp);
+        if (lane == 0 && w_ > worst) worst = w_;
+    }
+    note_error_warp(maxerr, worst);
 }
 
 // FactorGraph::update (code/graph.cpp:298-332) as ONE cooperative launch: every sweep is the two floods above with a
@@ -244,6 +400,10 @@ struct FgArgs {
     double *f2v, *v2f, *tmp;
     int n_small, n_big;
     const int32_t *small_edges, *big_edges;
+    const uint2 *a_hdr;
+    const uint32_t *a_nb;
+    const uint4 *b_hdr;
+    const uint32_t *b_terms;
     unsigned long long *err3;      // [3] max-error slots, [3] = sweeps (as uint32)
     uint32_t max_sweeps;
     double epsilon;
@@ -258,15 +418,24 @@ __global__ void __launch_bounds__(256) fg_update_kernel(const FgArgs a)
     for (; it < a.max_sweeps; ++it) {
         unsigned long long *err = a.err3 + it % 3;
         if (gtid == 0) a.err3[(it + 1) % 3] = 0ull;
-        for (int e = gtid; e < a.nedges; e += gthreads)
-            var_to_fac_edge(e, a.evar, a.card, a.moff, a.voff, a.vedges, a.f2v, a.v2f, err);
+        double worst = 0.0;
+        for (int e = gtid; e < a.nedges; e += gthreads) {
+            const double w_ = var_to_fac_rec(e, a.a_hdr, a.a_nb, a.moff, a.f2v, a.v2f);
+            if (w_ > worst) worst = w_;
+        }
+        note_error_warp(err, worst);
         grid.sync();
-        for (int i = gtid; i < a.n_small; i += gthreads)
-            fac_to_var_edge_small(a.small_edges[i], a.efac, a.evar, a.foff, a.card, a.moff, a.toff, a.estride, a.fsize, a.ftab,
-                                  a.v2f, a.f2v, a.tmp, err);
-        for (int i = gwarp; i < a.n_big; i += gwarps)
-            fac_to_var_edge(a.big_edges[i], lane, a.efac, a.evar, a.foff, a.card, a.moff, a.toff, a.estride, a.fsize, a.ftab,
-                            a.v2f, a.f2v, a.tmp, err);
+        worst = 0.0;
+        for (int i = gtid; i < a.n_small; i += gthreads) {
+            const double w_ = fac_to_var_rec(a.small_edges[i], a.b_hdr, a.b_terms, a.moff, a.ftab, a.v2f, a.f2v, a.tmp);
+            if (w_ > worst) worst = w_;
+        }
+        for (int i = gwarp; i < a.n_big; i += gwarps) {
+            const double w_ = fac_to_var_edge(a.big_edges[i], lane, a.efac, a.evar, a.foff, a.card, a.moff, a.toff, a.estride, a.fsize,
+                                              a.ftab, a.v2f, a.f2v, a.tmp);
+            if (lane == 0 && w_ > worst) worst = w_;
+        }
+        note_error_warp(err, worst);
         grid.sync();
         const double maxerror = __longlong_as_double((long long)*reinterpret_cast<volatile unsigned long long *>(err));
         if (maxerror < a.epsilon) break;          // code/graph.cpp:328, the same decision in every thread
@@ -351,8 +520,44 @@ int bnpp_fg_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfac, con
     std::vector<uint32_t> mvoff(nvars + 1, 0);
     for (int v = 0; v < nvars; ++v) mvoff[v + 1] = mvoff[v] + card[v];
     std::vector<int32_t> small_edges, big_edges;
-    for (int e = 0; e < nedges; ++e)
-        (fsize[efac[e]] / card[evar[e]] <= kSmallSub ? small_edges : big_edges).push_back(e);
+    for (int e = 0; e < nedges; ++e) {
+        const uint32_t r = card[evar[e]], sub = fsize[efac[e]] / r, w = (uint32_t)(foff[efac[e] + 1] - foff[efac[e]]);
+        (sub <= kSmallSub && r < 256 && w < 65536 ? small_edges : big_edges).push_back(e);
+    }
+    // records (see bnpp_fg): the reads of every update, resolved once
+    std::vector<uint2> a_hdr(nedges ? nedges : 1);
+    std::vector<uint32_t> a_nb;
+    for (int e = 0; e < nedges; ++e) {
+        const uint32_t v = evar[e];
+        a_hdr[e].x = (uint32_t)a_nb.size();
+        uint32_t n = 0;
+        for (int q = voff[v]; q < voff[v + 1]; ++q)
+            if (vedges[q] != e) {
+                a_nb.push_back(moff[vedges[q]]);
+                ++n;
+            }
+        if (n >= 65536 || card[v] >= 65536) return fail(ctx, BNPP_ETOOBIG, "factor graph: a variable with >= 65536 factors or values");
+        a_hdr[e].y = n | (card[v] << 16);
+    }
+    std::vector<uint4> b_hdr(nedges ? nedges : 1);
+    std::vector<uint32_t> b_terms;
+    for (int e : small_edges) {
+        const int f = efac[e], e0 = foff[f], w = foff[f + 1] - e0;
+        const uint32_t r = card[evar[e]], stj = estride[e], sub = fsize[f] / r;
+        b_hdr[e] = make_uint4(r | (sub << 8) | ((uint32_t)w << 16), (uint32_t)b_terms.size(), (uint32_t)toff[f], (uint32_t)(toff[f] >> 32));
+        for (uint32_t i = 0; i < r; ++i)
+            for (uint32_t ts = 0; ts < sub; ++ts) {
+                const uint32_t t = (ts / stj) * (stj * r) + i * stj + (ts % stj);
+                b_terms.push_back(t);
+                for (int u = 0; u < w; ++u) {
+                    const int eu = e0 + u;
+                    if (eu == e) continue;
+                    b_terms.push_back(moff[eu] + (t / estride[eu]) % card[evar[eu]]);
+                }
+            }
+    }
+    while (b_terms.size() % 4) b_terms.push_back(0);
+    if (a_nb.empty()) a_nb.push_back(0);
 
     bnpp_fg *g = new bnpp_fg();
     g->ctx = ctx;
@@ -366,6 +571,7 @@ int bnpp_fg_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfac, con
 #define UP(field, vec) if ((rc = to_device(ctx, &g->field, vec)) != BNPP_OK) { bnpp_fg_destroy(g); return rc; }
     UP(card, h_card) UP(foff, h_foff) UP(evar, evar) UP(efac, efac) UP(moff, moff) UP(voff, voff) UP(vedges, vedges)
     UP(toff, h_toff) UP(estride, estride) UP(fsize, fsize) UP(mvoff, mvoff) UP(small_edges, small_edges) UP(big_edges, big_edges)
+    UP(a_hdr, a_hdr) UP(a_nb, a_nb) UP(b_hdr, b_hdr) UP(b_terms, b_terms)
     g->n_small = (int)small_edges.size();
     g->n_big = (int)big_edges.size();
 #undef UP
@@ -414,6 +620,7 @@ int bnpp_fg_destroy(bnpp_fg *g)
     cudaFree(g->voff); cudaFree(g->vedges); cudaFree(g->toff); cudaFree(g->estride); cudaFree(g->fsize);
     cudaFree(g->mvoff); cudaFree(g->ftab); cudaFree(g->f2v); cudaFree(g->v2f); cudaFree(g->tmp);
     cudaFree(g->marg); cudaFree(g->maxerr); cudaFree(g->err3); cudaFree(g->small_edges); cudaFree(g->big_edges);
+    cudaFree(g->a_hdr); cudaFree(g->a_nb); cudaFree(g->b_hdr); cudaFree(g->b_terms);
     if (g->maxerr_host) cudaFreeHost(g->maxerr_host);
     if (g->sweeps_host) cudaFreeHost(g->sweeps_host);
     delete g;
@@ -425,11 +632,11 @@ static int fg_launch_sweep(bnpp_fg *g)
     bnpp_ctx *ctx = g->ctx;
     BNPP_CUDA(ctx, cudaMemsetAsync(g->maxerr, 0, sizeof(unsigned long long), ctx->stream));
     if (g->nedges) {
-        fg_var_to_fac_kernel<<<(g->nedges + 127) / 128, 128, 0, ctx->stream>>>(
-            g->nedges, g->evar, g->card, g->moff, g->voff, g->vedges, g->f2v, g->v2f, g->maxerr);
+        fg_var_to_fac_kernel<<<(g->nedges + 127) / 128, 128, 0, ctx->stream>>>(g->nedges, g->a_hdr, g->a_nb, g->moff, g->f2v, g->v2f,
+                                                                              g->maxerr);
         BNPP_CUDA(ctx, cudaGetLastError());
         fg_fac_to_var_kernel<<<(g->n_small + 32 * g->n_big + 127) / 128, 128, 0, ctx->stream>>>(
-            g->n_small, g->small_edges, g->n_big, g->big_edges, g->efac, g->evar, g->foff, g->card, g->moff, g->toff, g->estride, g->fsize, g->ftab, g->v2f,
+            g->n_small, g->small_edges, g->n_big, g->big_edges, g->b_hdr, g->b_terms, g->efac, g->evar, g->foff, g->card, g->moff, g->toff, g->estride, g->fsize, g->ftab, g->v2f,
             g->f2v, g->tmp, g->maxerr);
         BNPP_CUDA(ctx, cudaGetLastError());
         ctx->launches += 2;
@@ -464,6 +671,7 @@ int bnpp_fg_update(bnpp_fg *g, uint32_t max_sweeps, double epsilon, uint32_t *sw
         a.efac = g->efac; a.foff = g->foff; a.toff = g->toff; a.estride = g->estride; a.fsize = g->fsize;
         a.ftab = g->ftab; a.f2v = g->f2v; a.v2f = g->v2f; a.tmp = g->tmp; a.err3 = g->err3;
         a.n_small = g->n_small; a.n_big = g->n_big; a.small_edges = g->small_edges; a.big_edges = g->big_edges;
+        a.a_hdr = g->a_hdr; a.a_nb = g->a_nb; a.b_hdr = g->b_hdr; a.b_terms = g->b_terms;
         a.max_sweeps = max_sweeps;
         a.epsilon = epsilon;
         BNPP_CUDA(ctx, cudaMemsetAsync(g->err3, 0, 4 * sizeof(unsigned long long), ctx->stream));

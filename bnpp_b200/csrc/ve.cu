@@ -1044,12 +1044,14 @@ int upload_tasks(bnpp_ve_plan *pl, const double *const *tables_dev)
         pl->tasks_prog_dev = reinterpret_cast<uint32_t *>(p0);
         pl->tasks_tab_dev = reinterpret_cast<uint32_t *>(p1);
         pl->tasks_rec_dev = reinterpret_cast<TaskRecord *>(p2);
-        if (!pl->tasks_tab.empty())
-            BNPP_CUDA(ctx, cudaMemcpyAsync(pl->tasks_tab_dev, pl->tasks_tab.data(), pl->tasks_tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-        BNPP_CUDA(ctx, cudaMemcpyAsync(pl->tasks_rec_dev, pl->tasks_rec.data(), pl->tasks_rec.size() * sizeof(TaskRecord), cudaMemcpyHostToDevice, ctx->stream));
+        rc = stage_upload(ctx, pl->tasks_tab_dev, pl->tasks_tab.data(), pl->tasks_tab.size() * sizeof(uint32_t));
+        if (rc == BNPP_OK) rc = stage_upload(ctx, pl->tasks_rec_dev, pl->tasks_rec.data(), pl->tasks_rec.size() * sizeof(TaskRecord));
+        if (rc != BNPP_OK) return rc;
     }
-    if (moved)      // stream-ordered after any launch still reading the previous contents; the pageable source is staged before the call returns
-        BNPP_CUDA(ctx, cudaMemcpyAsync(pl->tasks_prog_dev, pl->tasks_prog.data(), pl->tasks_prog.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (moved) {    // stream-ordered after any launch still reading the previous contents
+        const int rc = stage_upload(ctx, pl->tasks_prog_dev, pl->tasks_prog.data(), pl->tasks_prog.size() * sizeof(uint32_t));
+        if (rc != BNPP_OK) return rc;
+    }
     pl->tasks_uploaded = true;
     for (auto &g : pl->groups) {
         if (g.launch_valid) continue;
