@@ -100,6 +100,7 @@ struct ParamsMVT {
     uint32_t soff[kMaxK];       // where operand k's range sits inside a stage (doubles, even)
     FastDiv dsplit;
     FastDiv div[kMaxR];
+    uint32_t so[kMaxR];         // output stride per outer axis (the plan may walk the outer axes in another order)
     uint32_t s_split[kMaxK];
     uint32_t s[kMaxK][kMaxR];
 };

@@ -343,6 +343,9 @@ int plan_mv(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *sx
         for (int a = std::max(split, 0); a < n; ++a)
             if (axes[a].s[heavy] && axes[a].s[heavy] < sx[heavy]) x_fast = false;
 
+    // the eliminated variable is a slow axis of the heavy operand: one output entry per thread with a loop over its values
+    // (contract_generic) already reads and writes whole rows of the fastest axes -- gathering through a table adds nothing
+    if (!x_fast) return 1;
     // the entry table: E real entries, then padding up to UB * kBlock that re-reads entry 0 into a spare stage slot
     const size_t slots = (size_t)UB * kBlock;
     const size_t words = slots * KP;

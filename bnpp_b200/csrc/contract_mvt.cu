@@ -61,7 +61,17 @@ __device__ __forceinline__ void mvt_produce(const ParamsMVT &p, uint32_t t, uint
         c = t - outer * p.n_split;
     }
     if (who == (uint32_t)K) {
-        meta[K] = outer * (p.ext_split * p.inner) + c * p.g * p.inner;
+        // the outer axes are walked in the PLAN's order (axes a large operand lacks fastest: its tile stays in L2), so
+        // the tile's place in the output comes from per-axis output strides
+        uint32_t ob = c * p.g * p.inner, rem = outer;
+#pragma unroll 1
+        for (int a = (int)p.R - 1; a > 0; --a) {
+            const uint32_t q = fastdiv(rem, p.div[a]);
+            ob += (rem - q * p.div[a].d) * p.so[a];
+            rem = q;
+        }
+        if (p.R > 0) ob += rem * p.so[0];
+        meta[K] = ob;
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
         return;
     }
@@ -235,7 +245,6 @@ int mvt_resident(bnpp_ctx *ctx, mvt_fn fn, unsigned smem)
 int plan_mvt(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *sx, const uint64_t *op_bytes,
              const std::vector<MVAxis> &axes, uint64_t n_out, const ParamsHead &h)
 {
-    (void)op_bytes;
     if (k < 1 || k > kMaxK || cx < 2 || cx > 64) return 1;
     const int n = (int)axes.size();
     for (int q = 0; q < k; ++q)
@@ -298,19 +307,39 @@ int plan_mvt(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *s
     const uint32_t T = (uint32_t)(inner * g);
     if (T < 64 && n_out > 4096) return 1;       // too few lanes per tile: the gather kernel
 
-    // outer axes (outside the split axis), neighbours that are contiguous in every operand merged
-    struct Outer { uint64_t ext; uint64_t s[kMaxK]; };
+    // outer axes (outside the split axis).  Above the tile the iteration order is the plan's: an axis that a large
+    // operand LACKS is walked fastest, so that operand's tile range is re-read from L2 instead of HBM (the output is
+    // addressed through per-axis strides, its layout is untouched).  Neighbours contiguous in every operand and in
+    // the output merge.
+    struct Outer { uint64_t ext; uint64_t s[kMaxK]; uint64_t so; uint64_t miss; };
+    std::vector<Outer> raw;
+    {
+        uint64_t so = (uint64_t)inner * ext_split;
+        for (int a = split - 1; a >= 0; --a) {
+            Outer o;
+            o.ext = axes[a].ext;
+            o.so = so;
+            o.miss = 0;
+            for (int q = 0; q < kMaxK; ++q) {
+                o.s[q] = q < k ? axes[a].s[q] : 0;
+                if (q < k && axes[a].s[q] == 0 && op_bytes[q] > (32ull << 20)) o.miss += op_bytes[q];
+            }
+            so *= axes[a].ext;
+            raw.insert(raw.begin(), o);
+        }
+        bool any = false;
+        for (const Outer &o : raw) any = any || o.miss != 0;
+        if (any) std::stable_sort(raw.begin(), raw.end(), [](const Outer &x, const Outer &y) { return x.miss < y.miss; });
+    }
     std::vector<Outer> outer;
-    for (int a = 0; a < split; ++a) {
-        Outer o;
-        o.ext = axes[a].ext;
-        for (int q = 0; q < kMaxK; ++q) o.s[q] = q < k ? axes[a].s[q] : 0;
+    for (const Outer &o : raw) {
         if (!outer.empty()) {
             Outer &up = outer.back();
-            bool ok = up.ext * o.ext < (1ull << 32);
+            bool ok = up.ext * o.ext < (1ull << 32) && up.so == o.so * o.ext;
             for (int q = 0; q < k && ok; ++q) ok = (up.s[q] == o.s[q] * o.ext);
             if (ok) {
                 up.ext *= o.ext;
+                up.so = o.so;
                 for (int q = 0; q < k; ++q) up.s[q] = o.s[q];
                 continue;
             }
@@ -334,6 +363,8 @@ int plan_mvt(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *s
     for (size_t a = 0; a < outer.size(); ++a) {
         p.div[a] = make_fastdiv((uint32_t)outer[a].ext);
         n_outer *= outer[a].ext;
+        if (outer[a].so >= (1ull << 32)) return 1;
+        p.so[a] = (uint32_t)outer[a].so;
         for (int q = 0; q < k; ++q) {
             if (outer[a].s[q] >= (1ull << 32)) return 1;
             p.s[q][a] = (uint32_t)outer[a].s[q];
