@@ -14,12 +14,20 @@ def launches(path):
     rows = [r for r in csv.reader(open(path)) if len(r) > 5]
     hdr = rows[0]
     ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    im = hdr.index("Metric Name") if "Metric Name" in hdr else None
+    iu = hdr.index("Metric Unit") if "Metric Unit" in hdr else None
     tot, cnt = collections.Counter(), collections.Counter()
     for r in rows[1:]:
+        if im is not None and r[im] != "gpu__time_duration.sum":
+            continue                     # a launch list may carry other metrics (DRAM bytes) beside the durations
         try:
             v = float(r[iv].replace(",", ""))
         except ValueError:
             continue
+        if iu is not None and r[iu] in ("us", "usecond"):
+            v *= 1e3
+        elif iu is not None and r[iu] in ("ms", "msecond"):
+            v *= 1e6
         name = r[ik].split("(bnpp::")[0].replace("void ", "").replace("bnpp::", "")
         tot[name] += v
         cnt[name] += 1
