@@ -396,30 +396,19 @@ class BN:
         if p is None:
             p = MarPlan(self.ctx, self.cards, self.scopes, observed, order, _arr=self._scope_arr)
             self._plans[key] = p
-        L = self.ctx.L
         n = max(1, p.result_size)
+        z_rank, _ = self.partition(full, heuristic)            # this rank's slab: P(evidence, shard variables = its values)
         with torch.cuda.stream(self.ctx.torch_stream):
-            res = torch.zeros(n + comm.world, dtype=torch.float64, device=self._dev.device)
-        self.ctx.check(L.bnpp_ve_plan_set_normalize(p.h, 0))
-        try:
-            p.run(self.table_ptrs, [full[v] for v in observed], res.data_ptr(), None)
-        finally:
-            self.ctx.check(L.bnpp_ve_plan_set_normalize(p.h, 1))
-        # this rank's partition = the sum of any unobserved variable's unnormalised slice
-        probe = next((v for v in variables if p.size[v] == self.cards[v]), None)
-        with torch.cuda.stream(self.ctx.torch_stream):
-            if probe is None:
-                z, _ = self.partition(full, heuristic)
-                res[n + comm.rank] = z
-            else:
-                res[n + comm.rank] = res[p.off[probe]:p.off[probe] + p.size[probe]].sum()
-        comm.allreduce_sum(res.data_ptr(), n + comm.world)          # the cross-shard sum-out (slices) + every rank's Z
-        L.bnpp_mar_plan_normalize.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-        self.ctx.check(L.bnpp_mar_plan_normalize(p.h, ctypes.c_void_p(res.data_ptr())))
+            res = torch.zeros(n + 1 + comm.world, dtype=torch.float64, device=self._dev.device)
+            res[n] = z_rank
+            res[n + 1 + comm.rank] = z_rank
+        # slices weighted by the rank's partition, summed over NVLink, divided by the total (bnpp_ve_plan_run_sharded)
+        comm.run_sharded(p, self.table_ptrs, [full[v] for v in observed], res.data_ptr(), res.data_ptr() + 8 * n)
+        comm.allreduce_sum(res.data_ptr() + 8 * (n + 1), comm.world)      # every rank's Z, for the shard variables' own marginals
         self.ctx.sync()
         host = res.cpu().numpy()
         out = [host[o:o + s_].copy() for o, s_ in zip(p.off, p.size)]
-        zr = host[n:n + comm.world]
+        zr = host[n + 1:n + 1 + comm.world]
         for v in shard_vars:
             m = np.zeros(self.cards[v])
             for r in range(comm.world):

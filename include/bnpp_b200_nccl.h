@@ -27,10 +27,12 @@ int bnpp_shard_allreduce_sum(bnpp_ctx *ctx, void *nccl_comm, double *buf_dev, ui
  * observed ids, obs_val holds the evidence values and THIS RANK's values of the shard variables.  Every
  * rank runs its slab, then the result tables (bnpp_ve_plan_result_size doubles: the scalar P(e) for a
  * partition plan, a table over the kept variables otherwise) and *z_dev are summed over all ranks in place
- * -- the cross-shard sum-out -- so every rank ends with the result of the unsharded query.  A marginals
- * plan is run unnormalised, summed, then normalised; the slices of the shard variables themselves hold 1
- * (each rank sees them observed): their marginals follow from the ranks' partitions.  Asynchronous on the
- * context's stream. */
+ * -- the cross-shard sum-out -- so every rank ends with the result of the unsharded query.
+ * A marginals plan returns normalised slices, so for it *z_dev must hold THIS RANK's partition
+ * P(evidence, shard variables = its values) on entry (run the rank's partition plan first): the slices are weighted
+ * by it, summed over the ranks and divided by the sum of the partitions (*z_dev on return).  The slices of the shard
+ * variables themselves hold 1 (each rank sees them observed): their marginals follow from the ranks' partitions.
+ * Asynchronous on the context's stream. */
 int bnpp_ve_plan_run_sharded(bnpp_ctx *ctx, bnpp_ve_plan *plan, void *nccl_comm, const double *const *tables_dev,
                              const uint32_t *obs_val, double *result_dev, double *z_dev);
 
