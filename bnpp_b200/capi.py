@@ -27,6 +27,7 @@ EXPORTS = [
     "bnpp_ve_plan_step_stats", "bnpp_ve_plan_step_kernel", "bnpp_ve_plan_set_fused", "bnpp_ve_plan_fused_info", "bnpp_ve_plan_fused_program", "bnpp_ve_plan_describe", "bnpp_ve_plan_set_segments", "bnpp_ve_plan_segments", "bnpp_ve_plan_segment_program", "bnpp_mar_plan_create", "bnpp_mar_plan_layout", "bnpp_pick_shard_vars",
     "bnpp_tuning_set", "bnpp_tuning_get", "bnpp_ve_plan_result_size", "bnpp_ve_plan_set_normalize",
     "bnpp_mar_plan_normalize", "bnpp_fg_reset", "bnpp_ve_plan_launches",
+    "bnpp_sampler_create", "bnpp_sampler_destroy", "bnpp_sampler_logical", "bnpp_sampler_likelihood",
 ]
 
 

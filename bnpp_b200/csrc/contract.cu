@@ -463,35 +463,74 @@ __global__ void __launch_bounds__(kBlock, 2) contract_staged(const __grid_consta
     }
     // Tile entry `slot = tid + 256 * i` lives at operand offset scatter(tid) + scatter(256 * i)
     // (disjoint bits): the first term is this thread's, the second is shared by the CTA.
-    __shared__ uint32_t s_off[16];
-    uint32_t my_off = 0;
-    for (int f = 0; f < (int)st.nlf; ++f) my_off += ((threadIdx.x >> st.lf[f].sh) & st.lf[f].mask) * st.lf[f].mul;
+    __shared__ uint32_t s_off[16], s_off2[8];
+    uint32_t my_off = 0, my_off2 = 0;
+    for (int f = 0; f < (int)st.nlf; ++f) {
+        my_off += ((threadIdx.x >> st.lf[f].sh) & st.lf[f].mask) * st.lf[f].mul;
+        my_off2 += (((2u * threadIdx.x) >> st.lf[f].sh) & st.lf[f].mask) * st.lf[f].mul;      // pair copies: slot 2 * tid
+    }
     if (threadIdx.x < 16) {
         const uint32_t slot = threadIdx.x * kBlock;
-        uint32_t o = 0;
-        for (int f = 0; f < (int)st.nlf; ++f) o += ((slot >> st.lf[f].sh) & st.lf[f].mask) * st.lf[f].mul;
+        uint32_t o = 0, o2 = 0;
+        for (int f = 0; f < (int)st.nlf; ++f) {
+            o += ((slot >> st.lf[f].sh) & st.lf[f].mask) * st.lf[f].mul;
+            o2 += (((2u * slot) >> st.lf[f].sh) & st.lf[f].mask) * st.lf[f].mul;                  // pair copies: block of 512 slots
+        }
         s_off[threadIdx.x] = o;
+        if (threadIdx.x < 8) s_off2[threadIdx.x] = o2;
     }
     __syncthreads();
     const uint32_t n_copy = (st.tile + kBlock - 1) / kBlock;
     const uint32_t tile_base = (uint32_t)__cvta_generic_to_shared(tile);
     const uint32_t n_chunks = (uint32_t)(h.n_items / CH);
     double zacc = 0.0;
-    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    // the chunk's base offsets are the same for the whole CTA and, for a transposed operand, a sum over two dozen
+    // one-bit fields: thread k computes operand k's (thread K the output's) one chunk ahead, the CTA reads them
+    // after the barrier that ends the previous chunk
+    __shared__ uint32_t s_hi[2][kMaxK + 1];
+    auto chunk_base = [&](uint32_t c, uint32_t *dst) {
+        const uint32_t who = threadIdx.x;
+        if (who <= (uint32_t)K) {
+            uint32_t o = 0;
+            const uint32_t item = c * CH;
+            for (int f = 0; f < (int)p.nf[who]; ++f) o += ((item >> p.f[who][f].sh) & p.f[who][f].mask) * p.f[who][f].mul;
+            dst[who] = o;
+        }
+    };
+    if (blockIdx.x < n_chunks) chunk_base(blockIdx.x, s_hi[0]);
+    __syncthreads();
+    uint32_t buf = 0;
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x, buf ^= 1u) {
+        if (c + gridDim.x < n_chunks) chunk_base(c + gridDim.x, s_hi[buf ^ 1u]);
         uint32_t hi[K], ohi;
-        decompose<K>(p, c * CH, hi, ohi);
+#pragma unroll
+        for (int k = 0; k < K; ++k) hi[k] = s_hi[buf][k];
+        ohi = s_hi[buf][K];
         const double *src = h.in[0];
         uint32_t base = 0;
 #pragma unroll
         for (int k = 0; k < K; ++k)
             if (k == sk) { src = h.in[k]; base = hi[k]; }
+        const double *src2 = src + base + my_off2;
         src += base + my_off;
-        // global -> shared without passing through registers (LDGSTS), 8 bytes per copy
-        for (uint32_t i = 0; i < n_copy; ++i) {
-            const uint32_t slot = threadIdx.x + i * kBlock;
-            if (slot < st.tile) {
-                const uint32_t dst = tile_base + 8u * (slot ^ ((slot >> st.swz) & 31u));
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + s_off[i]) : "memory");
+        // global -> shared without passing through registers (LDGSTS): 16 bytes per copy when slots 2m, 2m+1 are
+        // neighbours in the operand (its stride-1 axis is slot bit 0; the swizzle leaves bit 0 alone), else 8
+        if (st.pair) {
+            for (uint32_t i = 0; i < n_copy; i += 2) {
+                // thread t moves the pair of slots 2t, 2t+1 of every 512-slot block
+                const uint32_t slot = 2u * threadIdx.x + i * kBlock;
+                if (slot < st.tile) {
+                    const uint32_t dst = tile_base + 8u * (slot ^ (((slot >> st.swz) & 15u) << 1));
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src2 + s_off2[i >> 1]) : "memory");
+                }
+            }
+        } else {
+            for (uint32_t i = 0; i < n_copy; ++i) {
+                const uint32_t slot = threadIdx.x + i * kBlock;
+                if (slot < st.tile) {
+                    const uint32_t dst = tile_base + 8u * (slot ^ (((slot >> st.swz) & 15u) << 1));
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src + s_off[i]) : "memory");
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -515,7 +554,7 @@ __global__ void __launch_bounds__(kBlock, 2) contract_staged(const __grid_consta
 #pragma unroll
                 for (int x = 0; x < C; ++x) {
                     const uint32_t slot = slo[u] + j * st.slot_j + x * st.slot_x;
-                    acc[u][j][x] = tile[slot ^ ((slot >> st.swz) & 31u)];
+                    acc[u][j][x] = tile[slot ^ (((slot >> st.swz) & 15u) << 1)];
                 }
         bool zd = false;
         ApplyOperandsStaged<K, C, V, U>::run(raw, h.cls, acc, zd, sk);
@@ -1166,6 +1205,13 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
             for (int i = 0; i < 5; ++i)
                 if (rank_of_item[i] >= 0 && rank_of_item[i] < low) low = rank_of_item[i];
             st.swz = (low >= 5 && low < 32) ? (uint32_t)low : 31u;
+            // 16-byte tile copies: slot bit 0 is the operand's stride-1 axis, every other slot bit moves by an even
+            // number of doubles, and the table is 16-byte aligned (the chunk's base offset is then even too)
+            st.pair = (!loc.empty() && loc[0].stride == 1 && st.tile >= 2 * kBlock && aligned(ops[staged].data, 16)) ? 1 : 0;
+            for (size_t r = 1; r < loc.size() && st.pair; ++r)
+                if (loc[r].stride % 2) st.pair = 0;
+            for (uint32_t a = 0; a < R && st.pair; ++a)
+                if (m[a].s[staged] % 2 && m[a].s[staged] != 1) st.pair = 0;
             staged_fn fn = ok ? pick_staged(k, C) : nullptr;
             if (fn) {
                 desc->p2 = true;

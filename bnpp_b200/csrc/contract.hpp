@@ -56,7 +56,8 @@ struct StageInfo {
     int32_t sk;                 // staged operand
     uint32_t tile;              // tile entries (power of two, <= 4096)
     uint32_t slot_j, slot_x;    // slot stride of the V bit and of the eliminated variable (0 = independent)
-    uint32_t swz;               // bank swizzle: phys = slot ^ ((slot >> swz) & 31); the lanes differ in slot bits >= swz
+    uint32_t swz;               // bank swizzle: phys = slot ^ (((slot >> swz) & 15) << 1); the lanes differ in slot bits >= swz
+    uint32_t pair;              // tile copies move 16 bytes (slots 2m, 2m+1 are neighbours in the operand)
     uint8_t nlf, ncf;
     Field lf[12], cf[12];
 };

@@ -5,6 +5,7 @@
 #include <cassert>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <iostream>
 
 namespace bn {
@@ -528,7 +529,7 @@ FactorGraph BN::sum_product(void) const
     return g;
 }
 
-// ---- stochastic inference: out of the hot path, kept so the -ls/-lw/-gs flags work ----
+// ---- stochastic inference: -ls / -lw draw their samples on the GPU; -gs (one sequential chain) stays on the host ----
 std::vector<const Factor*> BN::topological_sampling_order() const
 {
     std::vector<const Factor*> order;
@@ -557,45 +558,66 @@ std::unordered_map<unsigned,unsigned> BN::sampling() const
     return valuation;
 }
 
+// The sampler of the C ABI (csrc/sampling.cu): one GPU thread per sample over the resident CPTs.  The seed comes from
+// BNPP_SEED (default 1): unlike the reference (std::random_device per draw) a run can be repeated.
+namespace {
+struct GpuSampler {
+    bnpp_sampler *h = nullptr;
+    std::vector<uint32_t> ev_var, ev_val;
+    uint64_t seed = 1;
+    GpuSampler(const BN &bn, const std::vector<Variable*> &variables, const std::vector<Factor*> &factors,
+               const std::vector<const Factor*> &order, const std::unordered_map<unsigned,unsigned> &evidence)
+    {
+        const int n = (int)variables.size();
+        std::vector<uint32_t> card(n), ord;
+        std::vector<std::vector<uint32_t>> ids(n), cards(n);
+        std::vector<bnpp_scope> scopes(n);
+        std::vector<const double*> tables(n);
+        for (int v = 0; v < n; ++v) {
+            card[v] = variables[v]->size();
+            const Domain &d = factors[v]->domain();
+            for (unsigned i = 0; i < d.width(); ++i) {
+                ids[v].push_back(d[i]->id());
+                cards[v].push_back(d[i]->size());
+            }
+            scopes[v] = bnpp_scope{(int32_t)d.width(), ids[v].data(), cards[v].data()};
+            tables[v] = factors[v]->device_data();
+        }
+        for (const Factor *pf : order) ord.push_back(pf->domain()[0]->id());
+        gpu::check(bnpp_sampler_create(gpu::ctx(), n, card.data(), scopes.data(), ord.data(), tables.data(), &h), "bnpp_sampler_create");
+        for (const auto &e : evidence) {
+            ev_var.push_back(e.first);
+            ev_val.push_back(e.second);
+        }
+        if (const char *s = std::getenv("BNPP_SEED")) seed = std::strtoull(s, nullptr, 10);
+        (void)bn;
+    }
+    ~GpuSampler() { bnpp_sampler_destroy(h); }
+};
+}  // namespace
+
+// BN::logical_sampling, code/model.cpp:540-560
 double BN::logical_sampling(const std::unordered_map<unsigned,unsigned> &evidence, double delta, double epsilon) const
 {
     const unsigned long M = 3 * std::log(2 / delta) / std::pow(epsilon, 2) * 1 / 0.1;
-    unsigned long hits = 0;
-    for (unsigned long i = 0; i < M; ++i) {
-        const std::unordered_map<unsigned,unsigned> s = sampling();
-        bool ok = true;
-        for (const auto &e : evidence) ok = ok && s.at(e.first) == e.second;
-        hits += ok;
-    }
+    GpuSampler g(*this, _variables, _factors, topological_sampling_order(), evidence);
+    uint64_t hits = 0;
+    gpu::check(bnpp_sampler_logical(g.h, (int)g.ev_var.size(), g.ev_var.data(), g.ev_val.data(), M, g.seed, &hits), "bnpp_sampler_logical");
     return 1.0 * hits / M;
 }
 
+// BN::likelihood_weighting, code/model.cpp:620-690 (bounded-variance stopping rule)
 double BN::likelihood_weighting(const std::unordered_map<unsigned,unsigned> &evidence, double delta, double epsilon) const
 {
-    const std::vector<const Factor*> order = topological_sampling_order();
     double U = 1.0;
     for (const Factor *pf : _factors) U *= pf->max();
     const double Nstar = 4 * std::log(2 / delta) * (1 + epsilon) / std::pow(epsilon, 2);
-    double N = 0.0, M = 0.0;
-    while (N < Nstar) {
-        double W = 1.0;
-        std::unordered_map<unsigned,unsigned> valuation;
-        for (const Factor *pf : order) {
-            const unsigned id = pf->domain()[0]->id();
-            auto e = evidence.find(id);
-            if (e == evidence.end()) {
-                for (const auto &s : pf->sampling(valuation)) valuation[s.first] = s.second;
-            } else {
-                valuation[id] = e->second;
-                Factor f = pf->conditioning(valuation);
-                assert(f.size() == 1);
-                W *= f[0];
-            }
-        }
-        assert(W > 0.0);
-        N += W / U;
-        ++M;
-    }
+    GpuSampler g(*this, _variables, _factors, topological_sampling_order(), evidence);
+    double N = 0.0;
+    uint64_t M = 0;
+    gpu::check(bnpp_sampler_likelihood(g.h, (int)g.ev_var.size(), g.ev_var.data(), g.ev_val.data(), U, Nstar, 1u << 16, 1ull << 34, g.seed,
+                                       &N, &M), "bnpp_sampler_likelihood");
+    assert(N > 0.0);
     return U * N / M;
 }
 

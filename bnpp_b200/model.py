@@ -475,3 +475,64 @@ def from_uai_text(ctx, text):
         sz = int(next(it))
         factors.append((sc, np.array([float(next(it)) for _ in range(sz)])))
     return kind, BN(ctx, cards, factors)
+
+
+class Sampler:
+    """bnpp_sampler: forward sampling of a Bayesian network on the GPU (BN::logical_sampling / BN::likelihood_weighting,
+    code/model.cpp:540-690).  Factor i must be the CPT of variable i with the child first in its scope."""
+
+    def __init__(self, bn):
+        self.bn, self.ctx = bn, bn.ctx
+        L = self.ctx.L
+        P = ctypes.POINTER
+        L.bnpp_sampler_create.argtypes = [ctypes.c_void_p, ctypes.c_int, capi.c_u32p, P(capi.Scope), capi.c_u32p,
+                                          P(ctypes.c_void_p), P(ctypes.c_void_p)]
+        L.bnpp_sampler_destroy.argtypes = [ctypes.c_void_p]
+        L.bnpp_sampler_logical.argtypes = [ctypes.c_void_p, ctypes.c_int, capi.c_u32p, capi.c_u32p, ctypes.c_uint64,
+                                           ctypes.c_uint64, capi.c_u64p]
+        L.bnpp_sampler_likelihood.argtypes = [ctypes.c_void_p, ctypes.c_int, capi.c_u32p, capi.c_u32p, ctypes.c_double,
+                                              ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
+                                              ctypes.POINTER(ctypes.c_double), capi.c_u64p]
+        n = bn.nvars
+        assert len(bn.scopes) == n and all(sc[0] == v for v, sc in enumerate(bn.scopes)), "factor i must be the CPT of variable i"
+        # topological order: parents before children (any such order samples the same distribution)
+        order, done = [], set()
+        while len(order) < n:
+            before = len(order)
+            for v in range(n):
+                if v not in done and all(p in done for p in bn.scopes[v][1:]):
+                    order.append(v)
+                    done.add(v)
+            assert len(order) > before, "cyclic network"
+        od = capi._u32(order)
+        tp = (ctypes.c_void_p * n)(*bn.table_ptrs)
+        h = ctypes.c_void_p()
+        self.ctx.check(L.bnpp_sampler_create(self.ctx.h, n, ctypes.cast(bn._cards_arr, capi.c_u32p), bn._scope_arr,
+                                             ctypes.cast(od, capi.c_u32p), tp, ctypes.byref(h)))
+        self.h = h
+
+    def _ev(self, evidence):
+        ev = sorted(evidence.items())
+        return len(ev), capi._u32([e[0] for e in ev]), capi._u32([e[1] for e in ev])
+
+    def logical(self, evidence, n_samples, seed=1):
+        """-> estimate of P(evidence) = hits / n_samples"""
+        k, a, b = self._ev(evidence)
+        hits = ctypes.c_uint64()
+        self.ctx.check(self.ctx.L.bnpp_sampler_logical(self.h, k, ctypes.cast(a, capi.c_u32p), ctypes.cast(b, capi.c_u32p),
+                                                       int(n_samples), int(seed), ctypes.byref(hits)))
+        return hits.value / n_samples
+
+    def likelihood(self, evidence, u_bound, n_star, seed=1, batch=1 << 14, max_samples=1 << 30):
+        """-> (estimate of P(evidence) = U * N / M, samples used M)"""
+        k, a, b = self._ev(evidence)
+        n, m = ctypes.c_double(), ctypes.c_uint64()
+        self.ctx.check(self.ctx.L.bnpp_sampler_likelihood(self.h, k, ctypes.cast(a, capi.c_u32p), ctypes.cast(b, capi.c_u32p),
+                                                          float(u_bound), float(n_star), int(batch), int(max_samples), int(seed),
+                                                          ctypes.byref(n), ctypes.byref(m)))
+        return u_bound * n.value / m.value, m.value
+
+    def close(self):
+        if self.h:
+            self.ctx.L.bnpp_sampler_destroy(self.h)
+            self.h = None

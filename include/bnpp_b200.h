@@ -281,6 +281,26 @@ int bnpp_fg_reset(bnpp_fg *fg);
  * out_host[moff_var[v] .. +card[v]) with moff_var the exclusive prefix sum of card. */
 int bnpp_fg_marginals(bnpp_fg *fg, double *out_host);
 
+/* ---- forward sampling, code/model.cpp:540-690 over code/factor.cpp:257-288 ------------ */
+/* One thread per sample walks the variables in the reference's topological order (`order`, variable ids) and draws
+ * each from its CPT given the sampled parents -- Factor::sampling -- with a counter-based generator keyed by
+ * (seed, sample index): reproducible where the reference (std::random_device per draw) is not.
+ *   scopes[nvars]    : factor i is the CPT of variable i, scope[0] the child, then its parents (code/model.cpp:111-119)
+ *   tables_dev[nvars]: the resident CPT of every variable (at most 2048 variables of at most 255 values) */
+typedef struct bnpp_sampler bnpp_sampler;
+int bnpp_sampler_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, const bnpp_scope *scopes, const uint32_t *order,
+                        const double *const *tables_dev, bnpp_sampler **out);
+int bnpp_sampler_destroy(bnpp_sampler *s);
+/* BN::logical_sampling, code/model.cpp:540-560: *hits of n_samples forward samples agree with the evidence. */
+int bnpp_sampler_logical(bnpp_sampler *s, int n_ev, const uint32_t *ev_var, const uint32_t *ev_val, uint64_t n_samples,
+                         uint64_t seed, uint64_t *hits);
+/* BN::likelihood_weighting, code/model.cpp:620-690 (bounded variance): evidence variables are clamped, a sample
+ * weighs W = the product of their CPT entries; samples are consumed IN ORDER until the sum of W / u_bound reaches
+ * n_star (or max_samples).  *n_sum = that sum, *m = samples used; the estimate is u_bound * n_sum / m.  `batch`
+ * samples are drawn per launch; the answer does not depend on it. */
+int bnpp_sampler_likelihood(bnpp_sampler *s, int n_ev, const uint32_t *ev_var, const uint32_t *ev_val, double u_bound,
+                            double n_star, uint64_t batch, uint64_t max_samples, uint64_t seed, double *n_sum, uint64_t *m);
+
 #ifdef __cplusplus
 }
 #endif
