@@ -1048,7 +1048,15 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
     }
 
     const bool generic = (cx > 2);
-    if (generic && !divide && n_out * cx >= mv_min_entries()) {
+    // The tiled multi-valued kernels stream: they pay per union entry for bringing operand entries to the SM.  A step
+    // whose operands are all much smaller than its union table (an outer product of small tables) re-reads them from
+    // L1/L2 either way, and there the one-entry-per-thread kernel with its cached gathers is as fast or faster
+    // (Munin1's widest step: 0.41 ms against 0.67 ms) -- so the tiled kernels take a step only when its heaviest
+    // operand covers at least a sixteenth of the union table (Barley's widest step, 1/5: 0.023 ms -> 0.018 ms tiled).
+    uint64_t heaviest = 0;
+    for (int q = 0; q < k; ++q) heaviest = std::max(heaviest, op_bytes[q]);
+    const bool streams = heaviest * 16 >= 8 * n_out * cx || mv_min_entries() == 0;
+    if (generic && !divide && streams && n_out * cx >= mv_min_entries()) {
         // multi-valued elimination: the table-driven tile kernel (contract_mv.cu), in the output's own axis order
         std::vector<MVAxis> mva;
         for (int i = 0; i < wr; ++i) {

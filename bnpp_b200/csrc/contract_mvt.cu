@@ -101,6 +101,33 @@ __device__ __forceinline__ void mvt_produce(const ParamsMVT &p, uint32_t t, uint
     }
 }
 
+// A row of 2 * P doubles per thread at a pitch of 2 * P doubles puts the 8 lanes of a 128-bit shared load on 8 / P
+// distinct 16-byte columns (P = 2: 2-way, P = 4: 4-way bank conflicts).  Reading the pairs of a row in an order ROTATED
+// by R -- R differs between the lanes that would collide -- removes the conflicts; the products land in registers by
+// their own index, so the sum still runs over x = 0, 1, ... in the reference's order.
+template <int K, int P, int R>
+__device__ __forceinline__ double row_sum_rot(const double *const (&row)[K])
+{
+    double pr[2 * P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int pi = (i + R) % P;
+        double2 a = *reinterpret_cast<const double2 *>(row[0] + 2 * pi);
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+            const double2 b = *reinterpret_cast<const double2 *>(row[k] + 2 * pi);
+            a.x = __dmul_rn(a.x, b.x);
+            a.y = __dmul_rn(a.y, b.y);
+        }
+        pr[2 * pi] = a.x;
+        pr[2 * pi + 1] = a.y;
+    }
+    double acc = 0.0;
+#pragma unroll
+    for (int x = 0; x < 2 * P; ++x) acc = __dadd_rn(acc, pr[x]);
+    return acc;
+}
+
 // MODE 0: any stride of the eliminated variable.  MODE 1: every operand has it at stride 1 (the canonical layout):
 // immediate offsets.  MODE 2: stride 1, an even cardinality and every row on a 16-byte boundary: two values per
 // shared load (LDS.128) -- rows of an even number of doubles put the lanes of a warp on few banks, and the wider
@@ -140,7 +167,17 @@ __global__ void __launch_bounds__(kBlock) contract_mvt(const __grid_constant__ P
 #pragma unroll
             for (int k = 0; k < K; ++k) row[k] = stage + p.soff[k] + (rowtab[j * K + k] + s_meta[s][k]);
             double acc = 0.0;
-            if (MODE == 2) {
+            if (MODE == 2 && cx == 8) {
+                switch ((j >> 1) & 3u) {
+                case 0: acc = row_sum_rot<K, 4, 0>(row); break;
+                case 1: acc = row_sum_rot<K, 4, 1>(row); break;
+                case 2: acc = row_sum_rot<K, 4, 2>(row); break;
+                default: acc = row_sum_rot<K, 4, 3>(row); break;
+                }
+            } else if (MODE == 2 && cx == 4) {
+                if ((j >> 2) & 1u) acc = row_sum_rot<K, 2, 1>(row);
+                else acc = row_sum_rot<K, 2, 0>(row);
+            } else if (MODE == 2) {
 #pragma unroll 2
                 for (uint32_t x = 0; x < cx; x += 2) {
                     double2 a = *reinterpret_cast<const double2 *>(row[0] + x);

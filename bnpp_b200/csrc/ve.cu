@@ -794,14 +794,17 @@ int fused_pick(bnpp_ve_plan *pl, uint32_t nb)
     return G;
 }
 
-bool segments_default_on()
+// 0: off, 1: on, 2 (default): on for plans with at least kTasksMinSmall small steps -- cutting a plan into tasks is host
+// work (the step programs of the tasks, ~0.3 ms) that a query with a few dozen buckets never earns back
+int segments_default_mode()
 {
-    static const int on = [] {
+    static const int mode = [] {
         const char *e = getenv("BNPP_FUSED_SEGMENTS");
-        return (e && e[0] == '0') ? 0 : 1;
+        return !e ? 2 : (e[0] == '0' ? 0 : 1);
     }();
-    return on != 0;
+    return mode;
 }
+constexpr size_t kTasksMinSmall = 96;
 
 constexpr uint64_t kTaskMaxWork = 1ull << 16;       // union entries one task (one CTA) may walk: a few microseconds, like a launch
 
@@ -838,6 +841,15 @@ void build_levels(bnpp_ve_plan *pl)
 {
     if (pl->runs || pl->arena || pl->batch_runs || !pl->offtab_host.empty()) return;
     const size_t ns = pl->steps.size();
+    if (pl->segments_mode == 2) {
+        size_t n_small = 0;
+        for (const PlanStep &st : pl->steps) n_small += step_is_small(st);
+        if (n_small < kTasksMinSmall) {
+            pl->segments_mode = 0;      // this plan: one launch per bucket, in elimination order
+            return;
+        }
+        pl->segments_mode = 1;
+    }
     free_tasks(pl);
     pl->levels_built = true;
     if (ns < 2) {
@@ -1143,7 +1155,7 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
     pl->n_obs = n_obs;
     pl->obs_card.assign(n_obs, 0);
     pl->fused_mode = fused_default_on() ? 1 : 0;
-    pl->segments_mode = segments_default_on() ? 1 : 0;
+    pl->segments_mode = segments_default_mode();
 
     std::map<uint32_t, int> obs_index;
     for (int i = 0; i < n_obs; ++i) obs_index[obs_var[i]] = i;
@@ -1227,7 +1239,7 @@ int bnpp_mar_plan_create(bnpp_ctx *ctx, int nvars, const uint32_t *card, int nfa
     pl->n_obs = n_obs;
     pl->obs_card.assign(n_obs, 0);
     pl->fused_mode = fused_default_on() ? 1 : 0;
-    pl->segments_mode = segments_default_on() ? 1 : 0;
+    pl->segments_mode = segments_default_mode();
     pl->is_mar = true;
     std::map<uint32_t, int> obs_index;
     for (int i = 0; i < n_obs; ++i) obs_index[obs_var[i]] = i;
@@ -1516,7 +1528,7 @@ int bnpp_ve_plan_describe(const bnpp_ve_plan *pl, uint64_t *buf, uint64_t cap, u
 int bnpp_ve_plan_set_segments(bnpp_ve_plan *pl, int on, uint32_t max_steps)
 {
     if (!pl) return BNPP_EINVAL;
-    pl->segments_mode = on != 0;
+    pl->segments_mode = on != 0 ? 1 : 0;
     if (pl->graph_exec && pl->graph_groups != (on != 0)) {      // the replay graph was built the other way
         cudaGraphExecDestroy(pl->graph_exec);
         cudaGraphDestroy(pl->graph);

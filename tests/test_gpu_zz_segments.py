@@ -22,6 +22,8 @@ def ctx():
 
 
 def _pr(bn, ev, flag, segments, cut=0, fused=False):
+    """PR on a FRESH plan (tasks can only be cut before a plan's first run) -> (Z, launches of the query)"""
+    bn.drop_plans()
     variables = [v for v in range(bn.nvars) if v not in ev]
     order, _ = bn.order(variables, ev, flag)
     p = bn.plan(sorted(ev), order)
@@ -64,14 +66,20 @@ def test_segments_on_the_wide_synthetic_network(ctx):
 
 
 def test_tasks_are_the_default_and_replay_as_a_graph(ctx, golden_models):
-    """default settings: Water / andes / insurance plans run as a handful of launches, and the graph replays (runs 2..4)
-    give the same bits as the first run and as one launch per bucket"""
+    """default settings: a plan with many small buckets (andes: 218 of 224) runs as a handful of launches; a plan with a
+    few dozen buckets is cut into tasks only on request (Water, insurance).  The graph replays (runs 2..4) give the
+    same bits as the first run and as one launch per bucket"""
     from bnpp_b200 import model
-    for name in ["Water", "andes", "insurance"]:
+    for name, force in [("andes", False), ("Water", True), ("insurance", True)]:
         m = golden_models[name]
         bn = model.from_uai_text(ctx, m["uai"])[1]
         case = [c for c in m["pr"] if c["flag"] == "mf"][-1]
         ev = {int(k): v for k, v in case["evidence"].items()}
+        variables = [v for v in range(bn.nvars) if v not in ev]
+        order, _ = bn.order(variables, ev, "mf")
+        p = bn.plan(sorted(ev), order)
+        if force:
+            p.set_segments(True, 0)
         zs = []
         for run in range(4):
             ctx.sync()
@@ -79,9 +87,6 @@ def test_tasks_are_the_default_and_replay_as_a_graph(ctx, golden_models):
             z, _ = bn.partition(ev, "mf")
             zs.append(z)
             launches = ctx.launches - l0
-        variables = [v for v in range(bn.nvars) if v not in ev]
-        order, _ = bn.order(variables, ev, "mf")
-        p = bn.plan(sorted(ev), order)
         assert launches < p.n_launches / 2, (name, launches, p.n_launches)
         p.set_segments(False, 0)
         z_plain, _ = bn.partition(ev, "mf")
