@@ -741,8 +741,8 @@ static staged_fn pick_staged(int K, int C)
 template <class F>
 static uint64_t resident_ctas(bnpp_ctx *ctx, F fn)
 {
-    static std::map<const void *, int> cache;
-    const void *key = reinterpret_cast<const void *>(fn);
+    static std::map<std::pair<int, const void *>, int> cache;      // per device and variant
+    const auto key = std::make_pair(ctx->device, reinterpret_cast<const void *>(fn));
     auto it = cache.find(key);
     if (it == cache.end()) {
         int per_sm = 0;

@@ -320,7 +320,11 @@ int plan_mvt(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *s
                 stage += (r + 3) & ~(uint64_t)1;
                 useful += distinct;
             }
-            if (!ok || 2 * stage * 8 + T * k * 4 > smem_budget) continue;
+            static const uint64_t min_stages = [] {
+                const char *e = getenv("BNPP_MVT_MIN_STAGES");
+                return e ? (uint64_t)atoi(e) : 2ull;
+            }();
+            if (!ok || min_stages * stage * 8 + T * k * 4 > smem_budget) continue;
             const double lanes = (double)T / (double)(((T + kBlock - 1) / kBlock) * kBlock);
             const double amort = (double)E / (double)(E + 256);
             const double score = lanes * amort;

@@ -263,10 +263,17 @@ class BN:
         return elim_order(self.cards, self.scopes, variables, heuristic, observed=sorted(observed), _arr=self._scope_arr,
                           _cards=self._cards_arr)
 
+    MAX_PLANS = 64      # every plan keeps its device arena, offset tables and replay graph: the cache is bounded (oldest out)
+
     def plan(self, observed, order):
         key = (tuple(observed), tuple(order))
         p = self._plans.get(key)
         if p is None:
+            while len(self._plans) >= self.MAX_PLANS:
+                old_key = next(iter(self._plans))
+                old = self._plans.pop(old_key)
+                self._batch_plans = {k: v for k, v in self._batch_plans.items() if v is not old}
+                old.close()
             p = VEPlan(self.ctx, self.cards, self.scopes, observed, order, _arr=self._scope_arr)
             self._plans[key] = p
         return p
@@ -339,7 +346,10 @@ class BN:
     def partition_batch(self, observed, values, heuristic="mf", host_values=None):
         """PR for a batch of evidence sets sharing the observed ids (config 5).
         observed: sorted variable ids; values: torch.uint8 CUDA tensor [nb][len(observed)] (or pass
-        host_values, a pinned uint8 tensor, to include the H2D copy).  -> device tensor [nb] of Z."""
+        host_values, a pinned uint8 tensor, to include the H2D copy).  -> device tensor [nb] of Z.
+        The returned tensor is the model's result buffer for batches of nb sets, written on the context's stream:
+        synchronise (`ctx.sync()`) before reading it on another stream, and clone it if it must survive the next call
+        with the same nb (stable pointers are what lets the library replay the run as a graph)."""
         observed = list(observed)
         # one plan per (observed ids, heuristic): the order depends on the ids only, so repeated batches over the same
         # ids pay neither the host ordering nor the planning again (drop_plans() forgets it)
