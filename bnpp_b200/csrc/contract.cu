@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -572,6 +573,168 @@ __global__ void __launch_bounds__(kBlock, 2) contract_staged(const __grid_consta
     if (h.z) grid_sum_to(zacc, h.partials, h.ticket, h.z);
 }
 
+// The tiles brought in by the TMA engine (see ParamsP2T): cp.async.bulk global -> shared of whole runs, one run per
+// thread and operand, completion counted on the stage's mbarrier -- no per-element address arithmetic, no swizzle.  A
+// ring of S stages: the copies of the next S-1 chunks are in flight while this one is consumed (without that the
+// only bytes in flight are the current chunk's, and a step whose operands are all half the union table -- F-bcast --
+// is latency-bound: a chunk is 48 KB, two CTAs per SM).  What a thread needs to find its entries of a tile (one
+// index per item, the same for every chunk) lives in registers.  Products are taken in operand order.
+template <int K, int C, int k0 = 0>
+struct TmaApply {
+    static constexpr int U = 4, V = 2;
+    static __device__ __forceinline__ void run(const double *stage, const uint32_t (&idx)[U][K], const TmaOperand *t, uint32_t mask,
+                                               const double (&raw)[K][U][4], const uint8_t *cls, double (&acc)[U][V][C], bool &zd)
+    {
+        if ((mask >> k0) & 1u) {
+            const uint32_t dj = t[k0].dj, dx = t[k0].dx;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+#pragma unroll
+                    for (int x = 0; x < C; ++x) {
+                        const double v = stage[idx[u][k0] + j * dj + x * dx];
+                        acc[u][j][x] = (k0 == 0) ? v : __dmul_rn(acc[u][j][x], v);
+                    }
+        } else
+            apply_all<C, V, U, k0 == 0, false>(raw[k0], cls[k0], acc, zd);
+        TmaApply<K, C, k0 + 1>::run(stage, idx, t, mask, raw, cls, acc, zd);
+    }
+};
+template <int K, int C>
+struct TmaApply<K, C, K> {
+    static __device__ __forceinline__ void run(const double *, const uint32_t (&)[4][K], const TmaOperand *, uint32_t,
+                                               const double (&)[K][4][4], const uint8_t *, double (&)[4][2][C], bool &) {}
+};
+
+template <int K, int C>
+__global__ void __launch_bounds__(kBlock, 2) contract_staged_tma(const __grid_constant__ ParamsP2T pt)
+{
+    constexpr int U = 4, V = 2;
+    constexpr uint32_t CH = U * kBlock;
+    extern __shared__ __align__(16) double stages[];        // [S][stage_doubles]
+    __shared__ __align__(8) uint64_t s_full[kStagedMaxStages];
+    __shared__ uint32_t s_hi[4][kMaxK + 1];                 // chunk bases, a ring over the chunks in flight
+    const ParamsP2 &p = pt.b;
+    const ParamsHead &h = p.h;
+    const uint32_t mask = pt.mask;
+    const uint32_t S = pt.stages, D = S - 1u;
+    auto run_pos = [](const TmaOperand &t, uint32_t r) {
+        uint32_t o = 0;
+        for (int i = 0; i < (int)t.nrb; ++i) o |= ((r >> i) & 1u) << t.rpos[i];
+        return o;
+    };
+    // idx[u][k]: shared-memory index of item u's entry (V bit and x at 0) for a staged operand, else its offset inside the chunk
+    uint32_t idx[U][K], olo[U], run_off[K], run_dst[K];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint32_t local = threadIdx.x + u * kBlock;
+        decompose<K>(p, local, idx[u], olo[u]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (!((mask >> k) & 1u)) continue;
+            const TmaOperand &t = pt.t[k];
+            uint32_t sl = 0;
+            for (int f = 0; f < (int)t.ncf; ++f) sl += ((local >> t.cf[f].sh) & t.cf[f].mask) * t.cf[f].mul;
+            idx[u][k] = t.off + run_pos(t, sl >> t.rbits) * ((1u << t.rbits) + 2u) + (sl & ((1u << t.rbits) - 1u));
+        }
+    }
+    // A bulk copy is a warp-uniform instruction: a warp issues the copies of its lanes one after the other (about ten
+    // issue slots each), so runs are dealt round-robin over the WARPS -- this thread moves run `my_run` of every staged
+    // operand's tile; run_off: where that run starts in the operand, relative to the chunk's base
+    const uint32_t my_run = (threadIdx.x & 31u) * (kBlock / 32) + (threadIdx.x >> 5);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        run_off[k] = run_dst[k] = 0;
+        if (!((mask >> k) & 1u)) continue;
+        const TmaOperand &t = pt.t[k];
+        for (int f = 1; f < (int)t.nlf; ++f) run_off[k] += (((my_run << t.rbits) >> t.lf[f].sh) & t.lf[f].mask) * t.lf[f].mul;
+        run_dst[k] = t.off + run_pos(t, my_run) * ((1u << t.rbits) + 2u);
+    }
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_full[0]);
+    const uint32_t stage0 = (uint32_t)__cvta_generic_to_shared(stages);
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < S; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t n_chunks = (uint32_t)(h.n_items / CH);
+    // A chunk's base offsets are sums over up to two dozen bit-fields of the chunk index (a transposed operand has
+    // one field per variable).  Warp w <= K owns operand w (warp K the output), lane f its field f: one shift-mask-
+    // multiply per lane and a warp-wide integer add -- a serial loop here would keep the CTA waiting at the barrier.
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    Field mine = Field{0u, 0u, 0u};
+    if (warp <= (uint32_t)K && lane < p.nf[warp]) mine = p.f[warp][lane];
+    auto chunk_base = [&](uint32_t c, uint32_t *dst) {
+        if (warp <= (uint32_t)K && c < n_chunks) {
+            const uint32_t o = __reduce_add_sync(0xffffffffu, (((c * CH) >> mine.sh) & mine.mask) * mine.mul);
+            if (lane == 0) dst[warp] = o;
+        }
+    };
+    // the copies of chunk c into stage s: thread 0 announces the bytes, every thread moves its run of every staged operand
+    auto fetch = [&](uint32_t c, const uint32_t *hi, uint32_t s) {
+        if (c >= n_chunks) return;
+        const uint32_t bar = bar0 + 8u * s;
+        if (threadIdx.x == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(pt.stage_bytes) : "memory");
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (!((mask >> k) & 1u)) continue;
+            const TmaOperand &t = pt.t[k];
+            if (my_run < (t.tile >> t.rbits)) {
+                const double *src = h.in[k] + (hi[k] + run_off[k]);
+                const uint32_t dst = stage0 + 8u * (s * pt.stage_doubles + run_dst[k]);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(src), "r"(8u << t.rbits), "r"(bar)
+                             : "memory");
+            }
+        }
+    };
+    for (uint32_t d = 0; d <= D; ++d) chunk_base(blockIdx.x + d * gridDim.x, s_hi[d]);
+    __syncthreads();
+    for (uint32_t d = 0; d < D; ++d) fetch(blockIdx.x + d * gridDim.x, s_hi[d], d);
+    double zacc = 0.0;
+    uint32_t stage = 0, parity = 0, it = 0;
+    for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x, ++it) {
+        // chunk it + D goes into the stage consumed in the previous iteration; its bases were computed one iteration ago
+        fetch(c + D * gridDim.x, s_hi[(it + D) & 3u], stage == 0 ? D : stage - 1u);
+        chunk_base(c + (D + 1u) * gridDim.x, s_hi[(it + D + 1u) & 3u]);
+        uint32_t hi[K], ohi;
+#pragma unroll
+        for (int k = 0; k < K; ++k) hi[k] = s_hi[it & 3u][k];
+        ohi = s_hi[it & 3u][K];
+        double raw[K][U][4];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if ((mask >> k) & 1u) continue;
+            uint32_t off[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) off[u] = hi[k] + idx[u][k];
+            issue_loads_all<C, V, U>(h.in[k], off, h.sx[k], h.sl[k], h.cls[k], raw[k]);
+        }
+        {
+            const uint32_t bar = bar0 + 8u * stage;
+            asm volatile("{\n.reg .pred P1;\nSTT_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra STT_DONE;\nbra STT_WAIT;\nSTT_DONE:\n}"
+                         ::"r"(bar), "r"(parity)
+                         : "memory");
+        }
+        double acc[U][V][C];
+        bool zd = false;
+        TmaApply<K, C>::run(stages + stage * pt.stage_doubles, idx, pt.t, mask, raw, h.cls, acc, zd);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const double r0 = (C == 2) ? __dadd_rn(acc[u][0][0], acc[u][0][C - 1]) : acc[u][0][0];
+            const double r1 = (C == 2) ? __dadd_rn(acc[u][1][0], acc[u][1][C - 1]) : acc[u][1][0];
+            double *o = h.out + (ohi + olo[u]);
+            zacc = __dadd_rn(zacc, __dadd_rn(r0, r1));
+            if (h.out_vec) *reinterpret_cast<double2 *>(o) = make_double2(r0, r1);
+            else { o[0] = r0; o[h.sol] = r1; }
+        }
+        __syncthreads();        // the stage is consumed (the next iteration's copies land in it); s_hi is written
+        if (++stage == S) { stage = 0; parity ^= 1u; }
+    }
+    if (h.z) grid_sum_to(zacc, h.partials, h.ticket, h.z);
+}
+
 // Generic path: any cardinality of the eliminated variable, one output entry per item.
 template <class P, int K, bool DIV>
 __global__ void __launch_bounds__(kBlock) contract_generic(const __grid_constant__ P p)
@@ -738,6 +901,20 @@ static staged_fn pick_staged(int K, int C)
 }
 
 // persistent grid: as many CTAs as are co-resident (occupancy is register-bound and differs per variant)
+typedef void (*tma_fn)(const ParamsP2T);
+static tma_fn pick_staged_tma(int K, int C)
+{
+    switch (K * 2 + (C - 1)) {
+    case 1 * 2 + 0: return contract_staged_tma<1, 1>;
+    case 1 * 2 + 1: return contract_staged_tma<1, 2>;
+    case 2 * 2 + 0: return contract_staged_tma<2, 1>;
+    case 2 * 2 + 1: return contract_staged_tma<2, 2>;
+    case 3 * 2 + 0: return contract_staged_tma<3, 1>;
+    case 3 * 2 + 1: return contract_staged_tma<3, 2>;
+    default: return nullptr;
+    }
+}
+
 template <class F>
 static uint64_t resident_ctas(bnpp_ctx *ctx, F fn)
 {
@@ -747,6 +924,27 @@ static uint64_t resident_ctas(bnpp_ctx *ctx, F fn)
     if (it == cache.end()) {
         int per_sm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+        it = cache.insert({key, per_sm}).first;
+    }
+    return (uint64_t)ctx->sm_count * it->second;
+}
+
+// the same for a kernel with dynamic shared memory (opt-in above 48 KB, granted once per device and variant); 0 on error
+template <class F>
+static uint64_t resident_ctas_dyn(bnpp_ctx *ctx, F fn, unsigned smem)
+{
+    static std::map<std::tuple<int, const void *, unsigned>, int> cache;       // per device, variant and KB of shared memory
+    static std::map<std::pair<int, const void *>, bool> granted;
+    const void *f = reinterpret_cast<const void *>(fn);
+    if (!granted[{ctx->device, f}]) {
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226u * 1024u)) != cudaSuccess) return 0;
+        granted[{ctx->device, f}] = true;
+    }
+    const auto key = std::make_tuple(ctx->device, f, (smem + 1023u) / 1024u);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kBlock, smem) != cudaSuccess || per_sm < 1) return 0;
         it = cache.insert({key, per_sm}).first;
     }
     return (uint64_t)ctx->sm_count * it->second;
@@ -1026,6 +1224,18 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
                 bin.erase(bin.begin() + best);
                 bin.insert(bin.begin() + slot, ax);
             }
+            // The chunks in flight at one time (a few hundred CTAs, grid-stride) differ in the LOW chunk bits.  An axis
+            // the staged operand lacks re-reads its tile: as a low chunk bit the second read comes right after the first
+            // and hits L2; left among the slow axes it goes to DRAM again half a kernel later (F-bcast: +33% traffic).
+            for (int moved = 0, slot = 11; moved < 4 && slot < (int)bin.size(); ++moved, ++slot) {
+                int best = -1;
+                for (size_t a = slot; a < bin.size() && best < 0; ++a)
+                    if (bin[a].s[staged] == 0) best = (int)a;
+                if (best < 0) break;
+                const Axis ax = bin[best];
+                bin.erase(bin.begin() + best);
+                bin.insert(bin.begin() + slot, ax);
+            }
             it.assign(bin.rbegin(), bin.rend());
         }
     }
@@ -1083,6 +1293,8 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
         const int rc = plan_mv(ctx, desc, k, cx, sx, op_bytes, mva, n_out, hm);
         if (rc <= 0) return rc;     // planned, or an error; 1 = not applicable: the one-entry-per-thread kernel below
     }
+    desc->smem = 0;
+    desc->mv = desc->mvt = desc->tma = false;
     const int C = generic ? 0 : (int)cx;
     int V = 1;
     if (!generic && !m.empty() && (m.back().ext % 2 == 0)) V = 2;
@@ -1176,55 +1388,151 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
             p.nf[q] = (uint8_t)nf;
         }
         if (fits && staged >= 0 && V == 2 && h.n_items % (4 * kBlock) == 0 && h.n_items >= 4 * kBlock) {
-            // slots of the tile: the chunk-local bits the staged operand depends on, ranked by ITS stride
+            // slots of a tile: the chunk-local bits operand q depends on, ranked by ITS stride.  tma: its runs can be
+            // bulk-copied (slot bit 0 is its stride-1 axis, every other bit and every chunk stride moves by an even number
+            // of doubles, the table is 16-byte aligned); *low: the lowest slot bit a lane bit drives
             struct Loc { uint64_t stride; int item_bit; };   // item_bit: -2 = x, -1 = V bit, 0..9 = item bits
-            std::vector<Loc> loc;
-            if (C == 2 && sx[staged]) loc.push_back({sx[staged], -2});
-            for (int a = 0; a <= 10; ++a)
-                if (bin[a].s[staged]) loc.push_back({bin[a].s[staged], a - 1});
-            std::sort(loc.begin(), loc.end(), [](const Loc &x, const Loc &y) { return x.stride < y.stride; });
+            int lane_rank[5];            // of the last build_stage call: slot bit each lane bit drives (-1: none)
+            auto build_stage = [&](int q, StageInfo &st, bool &even, int &low) -> bool {
+                std::vector<Loc> loc;
+                if (C == 2 && sx[q]) loc.push_back({sx[q], -2});
+                for (int a = 0; a <= 10; ++a)
+                    if (bin[a].s[q]) loc.push_back({bin[a].s[q], a - 1});
+                std::sort(loc.begin(), loc.end(), [](const Loc &x, const Loc &y) { return x.stride < y.stride; });
+                memset(&st, 0, sizeof st);
+                st.sk = q;
+                st.tile = 1u << loc.size();
+                bool ok = loc.size() <= 12;
+                int rank_of_item[10];
+                for (int i = 0; i < 10; ++i) rank_of_item[i] = -1;
+                for (size_t r = 0; r < loc.size() && ok; ++r) {
+                    if (loc[r].item_bit == -2) st.slot_x = 1u << r;
+                    else if (loc[r].item_bit == -1) st.slot_j = 1u << r;
+                    else rank_of_item[loc[r].item_bit] = (int)r;
+                    // tile-load fields: runs of ranks whose strides keep doubling
+                    if (st.nlf && loc[r].stride == ((uint64_t)st.lf[st.nlf - 1].mul << ilog2(st.lf[st.nlf - 1].mask + 1)))
+                        st.lf[st.nlf - 1].mask = (st.lf[st.nlf - 1].mask << 1) | 1u;
+                    else if (st.nlf < 12) st.lf[st.nlf++] = Field{1u, (uint32_t)loc[r].stride, (uint32_t)r};
+                    else ok = false;
+                }
+                // consumption fields: runs of item bits whose ranks are consecutive
+                for (int i = 0; i < 10 && ok; ++i) {
+                    if (rank_of_item[i] < 0) continue;
+                    if (st.ncf && i > 0 && rank_of_item[i - 1] >= 0 && rank_of_item[i] == rank_of_item[i - 1] + 1 &&
+                        st.cf[st.ncf - 1].sh + ilog2(st.cf[st.ncf - 1].mask + 1) == (uint32_t)i)
+                        st.cf[st.ncf - 1].mask = (st.cf[st.ncf - 1].mask << 1) | 1u;
+                    else if (st.ncf < 12) st.cf[st.ncf++] = Field{1u, 1u << rank_of_item[i], (uint32_t)i};
+                    else ok = false;
+                }
+                low = 32;
+                for (int i = 0; i < 5; ++i) {
+                    lane_rank[i] = rank_of_item[i];
+                    if (rank_of_item[i] >= 0 && rank_of_item[i] < low) low = rank_of_item[i];
+                }
+                even = !loc.empty() && loc[0].stride == 1 && aligned(ops[q].data, 16);
+                for (size_t r = 1; r < loc.size() && even; ++r)
+                    if (loc[r].stride % 2) even = false;
+                for (uint32_t a = 0; a < R && even; ++a)
+                    if (m[a].s[q] % 2 && m[a].s[q] != 1) even = false;
+                return ok;
+            };
+            // TMA: runs of at least 64 bytes, at most one run per thread
+            auto tma_operand = [&](const StageInfo &st, bool even, TmaOperand &t) -> bool {
+                if (!even || !st.nlf || st.lf[0].mul != 1 || st.lf[0].sh != 0) return false;
+                const uint32_t rb = ilog2(st.lf[0].mask + 1);
+                if (rb < 3 || (st.tile >> rb) > (uint32_t)kBlock) return false;
+                memset(&t, 0, sizeof t);
+                t.tile = st.tile;
+                t.rbits = rb;
+                // run positions: the run bits the lanes drive lowest (in the operand's own order), then the others
+                t.nrb = (uint8_t)(ilog2(st.tile) - rb);
+                bool placed[12] = {false};
+                int next = 0;
+                static const int order = [] { const char *e = getenv("BNPP_TMA_RUNORDER"); return e ? atoi(e) : 1; }();
+                if (order == 1) {
+                    for (int i = 0; i < 5; ++i)
+                        if (lane_rank[i] >= (int)rb) { t.rpos[lane_rank[i] - rb] = (uint8_t)next++; placed[lane_rank[i] - rb] = true; }
+                } else if (order == 2) {
+                    for (int i = 0; i < 5; ++i)
+                        if (lane_rank[i] >= (int)rb) placed[lane_rank[i] - rb] = true;
+                    for (int i = 0; i < (int)t.nrb; ++i)
+                        if (placed[i]) t.rpos[i] = (uint8_t)next++;
+                }
+                for (int i = 0; i < (int)t.nrb; ++i)
+                    if (!placed[i]) t.rpos[i] = (uint8_t)next++;
+                const uint32_t pitch = (1u << rb) + 2u;
+                auto phys = [&](uint32_t slot) {
+                    uint32_t r = 0;
+                    for (int i = 0; i < (int)t.nrb; ++i) r |= (((slot >> rb) >> i) & 1u) << t.rpos[i];
+                    return r * pitch + (slot & ((1u << rb) - 1u));
+                };
+                t.dj = phys(st.slot_j);
+                t.dx = phys(st.slot_x);
+                t.nlf = st.nlf;
+                t.ncf = st.ncf;
+                memcpy(t.lf, st.lf, sizeof t.lf);
+                memcpy(t.cf, st.cf, sizeof t.cf);
+                return true;
+            };
             StageInfo &st = desc->p2p.st;
-            st.sk = staged;
-            st.tile = 1u << loc.size();
-            bool ok = loc.size() <= 12;
-            int rank_of_item[10];
-            for (int i = 0; i < 10; ++i) rank_of_item[i] = -1;
-            for (size_t r = 0; r < loc.size() && ok; ++r) {
-                if (loc[r].item_bit == -2) st.slot_x = 1u << r;
-                else if (loc[r].item_bit == -1) st.slot_j = 1u << r;
-                else rank_of_item[loc[r].item_bit] = (int)r;
-                // tile-load fields: runs of ranks whose strides keep doubling
-                if (st.nlf && loc[r].stride == ((uint64_t)st.lf[st.nlf - 1].mul << ilog2(st.lf[st.nlf - 1].mask + 1)))
-                    st.lf[st.nlf - 1].mask = (st.lf[st.nlf - 1].mask << 1) | 1u;
-                else if (st.nlf < 12) st.lf[st.nlf++] = Field{1u, (uint32_t)loc[r].stride, (uint32_t)r};
-                else ok = false;
-            }
-            // consumption fields: runs of item bits whose ranks are consecutive
-            for (int i = 0; i < 10 && ok; ++i) {
-                if (rank_of_item[i] < 0) continue;
-                if (st.ncf && i > 0 && rank_of_item[i - 1] >= 0 && rank_of_item[i] == rank_of_item[i - 1] + 1 &&
-                    st.cf[st.ncf - 1].sh + ilog2(st.cf[st.ncf - 1].mask + 1) == (uint32_t)i)
-                    st.cf[st.ncf - 1].mask = (st.cf[st.ncf - 1].mask << 1) | 1u;
-                else if (st.ncf < 12) st.cf[st.ncf++] = Field{1u, 1u << rank_of_item[i], (uint32_t)i};
-                else ok = false;
-            }
-            // lanes are item bits 0..4: swizzle with the lowest slot bit any of them drives (if it is high enough)
+            bool even = false;
             int low = 32;
-            for (int i = 0; i < 5; ++i)
-                if (rank_of_item[i] >= 0 && rank_of_item[i] < low) low = rank_of_item[i];
+            const bool ok = build_stage(staged, st, even, low);
+            uint64_t blocks = h.n_items / (4 * kBlock);
+            ParamsP2T &pt = desc->p2t;
+            if (ok && staged_tma_enabled() && k <= kTmaMaxK && tma_operand(st, even, pt.t[staged])) {
+                pt.mask = 1u << staged;
+                static const uint32_t budget = [] { const char *e = getenv("BNPP_STAGED_BUDGET_KB"); return e ? (uint32_t)atoi(e) * 1024u : kStagedSmemBudget; }();
+                auto padded = [](const TmaOperand &t) { return t.tile + 2u * (t.tile >> t.rbits); };
+                uint32_t doubles = padded(pt.t[staged]);
+                // the other operands ride along while two stages of everything fit, smallest tile first
+                if (staged_async_enabled()) {
+                    std::vector<std::pair<uint32_t, int>> riders;
+                    for (int q = 0; q < k; ++q) {
+                        StageInfo sq;
+                        bool eq = false;
+                        int lq = 32;
+                        if (q != staged && build_stage(q, sq, eq, lq) && tma_operand(sq, eq, pt.t[q])) riders.push_back({padded(pt.t[q]), q});
+                    }
+                    std::sort(riders.begin(), riders.end());
+                    for (const auto &r : riders)
+                        if (2u * (doubles + r.first) * 8u <= budget) {
+                            doubles += r.first;
+                            pt.mask |= 1u << r.second;
+                        }
+                }
+                uint32_t off = 0;
+                pt.stage_bytes = 0;
+                for (int q = 0; q < k; ++q)
+                    if ((pt.mask >> q) & 1u) {
+                        pt.t[q].off = off;
+                        off += padded(pt.t[q]);
+                        pt.stage_bytes += pt.t[q].tile * 8u;
+                    }
+                pt.stage_doubles = off;
+                pt.stages = (3u * off * 8u <= budget) ? 3u : 2u;
+                tma_fn fn = pick_staged_tma(k, C);
+                if (fn && 2u * off * 8u <= budget) {
+                    pt.b = p;
+                    desc->p2 = true;
+                    desc->tma = true;
+                    desc->smem = pt.stages * off * (unsigned)sizeof(double);
+                    const uint64_t cap = resident_ctas_dyn(ctx, fn, desc->smem);
+                    if (!cap) return fail(ctx, BNPP_ECUDA, "contract_staged_tma: shared memory not granted");
+                    if (blocks > cap) blocks = cap;
+                    static const char *const names[8] = {"tma", "tma/0", "tma/1", "tma/01", "tma/2", "tma/02", "tma/12", "tma/012"};
+                    describe(desc, pt.b.h, reinterpret_cast<const void *>(fn), blocks, names[pt.mask & 7u], k, C, V, 4, false, false, R);
+                    return BNPP_OK;
+                }
+            }
+            // element-wise copies (LDGSTS).  Lanes are item bits 0..4: swizzle with the lowest slot bit any of them
+            // drives (if it is high enough); 16-byte copies when slots 2m, 2m+1 are neighbours in the operand
             st.swz = (low >= 5 && low < 32) ? (uint32_t)low : 31u;
-            // 16-byte tile copies: slot bit 0 is the operand's stride-1 axis, every other slot bit moves by an even
-            // number of doubles, and the table is 16-byte aligned (the chunk's base offset is then even too)
-            st.pair = (!loc.empty() && loc[0].stride == 1 && st.tile >= 2 * kBlock && aligned(ops[staged].data, 16)) ? 1 : 0;
-            for (size_t r = 1; r < loc.size() && st.pair; ++r)
-                if (loc[r].stride % 2) st.pair = 0;
-            for (uint32_t a = 0; a < R && st.pair; ++a)
-                if (m[a].s[staged] % 2 && m[a].s[staged] != 1) st.pair = 0;
+            st.pair = (even && st.tile >= 2 * kBlock) ? 1 : 0;
             staged_fn fn = ok ? pick_staged(k, C) : nullptr;
             if (fn) {
                 desc->p2 = true;
                 desc->staged = true;
-                uint64_t blocks = h.n_items / (4 * kBlock);
                 const uint64_t cap = resident_ctas(ctx, fn);
                 if (blocks > cap) blocks = cap;
                 describe(desc, p.h, reinterpret_cast<const void *>(fn), blocks, staged == 0 ? "staged0" : (staged == 1 ? "staged1" : "staged2"),

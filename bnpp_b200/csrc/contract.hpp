@@ -52,6 +52,8 @@ struct ParamsP2 {
 // the chunk needs into shared memory, reading along the operand's OWN fastest axes.
 //   slot -> operand offset : sum_f ((slot  >> sh) & mask) * mul   over lf   (tile load)
 //   item -> slot           : sum_f ((local >> sh) & mask) * mul   over cf   (consumption)
+constexpr uint32_t kStagedMaxStages = 3;
+constexpr uint32_t kStagedSmemBudget = 110u * 1024u;      // contract_staged_tma: two CTAs per SM
 struct StageInfo {
     int32_t sk;                 // staged operand
     uint32_t tile;              // tile entries (power of two, <= 4096)
@@ -64,6 +66,28 @@ struct StageInfo {
 struct ParamsP2S {
     ParamsP2 b;
     StageInfo st;
+};
+
+// The same tiling with the tiles brought in by the TMA engine (contract_staged_tma).  Ranked by an operand's own
+// strides, slots 0 .. 2^rbits - 1 of its tile are ONE contiguous run of it, so a tile is tile >> rbits bulk copies;
+// a run sits at (its run position) * (2^rbits + 2) doubles of the stage: with the 16-byte pad and the lane-driven run
+// bits lowest in the run position, the lanes of a warp that walk over runs meet two to a bank at worst.
+// Any operand whose runs are 16-byte aligned and at least 64 bytes long can come this way -- the transposed one
+// must, the others do when the ring of stages fits; the rest is loaded into registers chunk by chunk.
+constexpr int kTmaMaxK = 3;
+struct TmaOperand {
+    uint32_t tile, rbits;       // slots; log2 of the run length
+    uint32_t off;               // where the padded tile starts inside a stage (doubles, even)
+    uint32_t dj, dx;            // padded-tile distance of the V bit and of the eliminated variable (0 = independent)
+    uint8_t nlf, ncf;
+    uint8_t nrb, rpos[12];      // run r of the tile sits at run position sum_i bit_i(r) << rpos[i]: the run bits the LANES drive first
+    Field lf[12], cf[12];       // lf[0] is the run itself; lf[1..] place run r inside the operand
+};
+struct ParamsP2T {
+    ParamsP2 b;
+    uint32_t mask;              // operands that come through shared memory
+    uint32_t stages, stage_doubles, stage_bytes;     // ring depth (2..3); doubles per stage; bytes the copies of one stage move
+    TmaOperand t[kTmaMaxK];
 };
 
 // Multi-valued elimination (cardinality of the eliminated variable > 2), table driven.  A CTA owns TILES of T
@@ -113,10 +137,12 @@ struct LaunchDesc {
     bool staged = false;
     bool mv = false;            // contract_mv: params in mvp, dynamic shared memory `smem`, device table `mv_tab`
     bool mvt = false;           // contract_mvt: params in mvtp, same ownership of `mv_tab`
+    bool tma = false;           // contract_staged_tma: params in p2t, dynamic shared memory `smem`
     int k = 0;
     unsigned smem = 0;
     uint32_t *mv_tab = nullptr; // owned: freed by contract_release (stream-ordered)
     ParamsP2S p2p;              // .b is the plain power-of-two block
+    ParamsP2T p2t;
     ParamsMR mrp;
     ParamsMV mvp;
     ParamsMVT mvtp;
@@ -126,8 +152,8 @@ struct LaunchDesc {
     bool div = false, generic = false;
     uint32_t R = 0;
     std::string name();
-    ParamsHead &head() { return mvt ? mvtp.h : (mv ? mvp.h : (p2 ? p2p.b.h : mrp.h)); }
-    void *params() { return mvt ? static_cast<void *>(&mvtp) : mv ? static_cast<void *>(&mvp) : (p2 ? (staged ? static_cast<void *>(&p2p) : static_cast<void *>(&p2p.b)) : static_cast<void *>(&mrp)); }
+    ParamsHead &head() { return tma ? p2t.b.h : (mvt ? mvtp.h : (mv ? mvp.h : (p2 ? p2p.b.h : mrp.h))); }
+    void *params() { return tma ? static_cast<void *>(&p2t) : mvt ? static_cast<void *>(&mvtp) : mv ? static_cast<void *>(&mvp) : (p2 ? (staged ? static_cast<void *>(&p2p) : static_cast<void *>(&p2p.b)) : static_cast<void *>(&mrp)); }
 };
 
 int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scope *out_scope, int64_t elim_var,

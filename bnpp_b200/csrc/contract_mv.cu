@@ -190,12 +190,18 @@ struct MvKnobs {
     uint64_t min_entries;
     uint32_t emax;
     uint32_t staged = 1;
+    uint32_t staged_tma = 1;
+    uint32_t staged_async = 1;
     MvKnobs()
     {
         const char *e = getenv("BNPP_MV_MIN_ENTRIES");
         min_entries = e ? (uint64_t)strtoull(e, nullptr, 10) : (uint64_t)(1u << 15);
         e = getenv("BNPP_MV_EMAX");
         emax = e ? (uint32_t)atoi(e) : 0u;
+        e = getenv("BNPP_STAGED_TMA");
+        if (e && e[0] == '0') staged_tma = 0;
+        e = getenv("BNPP_STAGED_ASYNC");
+        if (e && e[0] == '0') staged_async = 0;
     }
 };
 static MvKnobs &knobs()
@@ -206,6 +212,8 @@ static MvKnobs &knobs()
 
 uint64_t mv_min_entries() { return knobs().min_entries; }
 bool mv_staged_enabled() { return knobs().staged != 0; }
+bool staged_tma_enabled() { return knobs().staged_tma != 0; }
+bool staged_async_enabled() { return knobs().staged_async != 0; }
 
 static uint32_t mv_emax(int k)
 {
@@ -426,6 +434,8 @@ extern "C" int bnpp_tuning_set(const char *key, uint64_t value)
     if (!strcmp(key, "mv_min_entries")) bnpp::knobs().min_entries = value;
     else if (!strcmp(key, "mv_emax")) bnpp::knobs().emax = (uint32_t)value;
     else if (!strcmp(key, "mv_staged")) bnpp::knobs().staged = (uint32_t)value;
+    else if (!strcmp(key, "staged_tma")) bnpp::knobs().staged_tma = (uint32_t)value;
+    else if (!strcmp(key, "staged_async")) bnpp::knobs().staged_async = (uint32_t)value;
     else return BNPP_EINVAL;
     return BNPP_OK;
 }
@@ -436,6 +446,8 @@ extern "C" int bnpp_tuning_get(const char *key, uint64_t *value)
     if (!strcmp(key, "mv_min_entries")) *value = bnpp::knobs().min_entries;
     else if (!strcmp(key, "mv_emax")) *value = bnpp::knobs().emax;
     else if (!strcmp(key, "mv_staged")) *value = bnpp::knobs().staged;
+    else if (!strcmp(key, "staged_tma")) *value = bnpp::knobs().staged_tma;
+    else if (!strcmp(key, "staged_async")) *value = bnpp::knobs().staged_async;
     else return BNPP_EINVAL;
     return BNPP_OK;
 }

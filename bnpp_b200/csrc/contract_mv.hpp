@@ -23,5 +23,7 @@ int plan_mv(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *sx
 int plan_mvt(bnpp_ctx *ctx, LaunchDesc *d, int k, uint32_t cx, const uint64_t *sx, const uint64_t *op_bytes,
              const std::vector<MVAxis> &axes, uint64_t n_out, const ParamsHead &h);
 bool mv_staged_enabled();
+bool staged_async_enabled();    // ... and the other operands prefetched by cp.async into thread-private slots
+bool staged_tma_enabled();      // transposed binary operands: tile by TMA bulk copies (contract_staged_bulk) or by LDGSTS
 
 }  // namespace bnpp

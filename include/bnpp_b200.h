@@ -85,7 +85,11 @@ int bnpp_last_launch(const bnpp_ctx *ctx, char *name, size_t name_len, uint32_t 
  *   "mv_emax"        : union entries per tile of the gather variant of that kernel (64..2048; 0 = default)
  *   "mv_staged"      : 1 (default) = operands whose tile footprint is a compact range are staged in shared memory
  *                      by bulk copies (contract_mvt); 0 = always the gather variant (contract_mv)
- * Unknown keys return BNPP_EINVAL.  Environment BNPP_MV_MIN_ENTRIES / BNPP_MV_EMAX seed the defaults. */
+ *   "staged_tma"     : 1 (default) = the tile of a transposed operand of a binary elimination comes in by bulk copies
+ *                      of its contiguous runs (contract_staged_bulk); 0 = element-wise cp.async (contract_staged)
+ *   "staged_async"   : 1 (default) = in that kernel the other operands are prefetched too (cp.async, a ring of stages)
+ *                      when their micro-tiles are at most two values; 0 = loaded into registers chunk by chunk
+ * Unknown keys return BNPP_EINVAL.  Environment BNPP_MV_MIN_ENTRIES / BNPP_MV_EMAX / BNPP_STAGED_TMA / BNPP_STAGED_ASYNC seed the defaults. */
 int bnpp_tuning_set(const char *key, uint64_t value);
 int bnpp_tuning_get(const char *key, uint64_t *value);
 

@@ -242,18 +242,41 @@ def test_transposed_operands_through_shared_memory(ctx):
         ([allv[:-1], allv[::-1], [3, 9]], 17),                  # K=3, the big reversed one in the middle
         ([allv[::-1], allv[2:]], 0),                            # the reversed operand first
     ]
-    for scopes, elim in cases:
-        ofs, dfs = [], []
-        for sc in scopes:
-            o, d = rand_factor(ctx, rng, sc, cards)
-            ofs.append(o); dfs.append(d)
-        out_scope = [v for v in allv if v != elim]
-        want = orc.product_sum_out(ofs, out_scope, elim, cards)
-        got = fused_product_sum_out(ctx, dfs, out_scope, elim)
-        seen.add(ctx.last_launch()[0].split(",")[0])
-        assert np.array_equal(got.values(), want.values), (scopes, elim, ctx.last_launch())
-        assert zclose(got.partition, want.partition)
-    assert any("staged" in s for s in seen), seen
+    from bnpp_b200 import capi
+    # operands whose contiguous runs inside a tile are short (8 doubles) or cut by the eliminated variable
+    mixed = allv[9:] + allv[:9]
+    cases += [
+        ([allv, mixed[::-1]], 4),
+        ([allv[6:] + allv[:6], allv], 12),
+        ([allv[3:][::-1] + allv[:3], allv], None),
+        ([allv[:17], allv[::-1]], 3),                           # A lacks the innermost output axis: scalar loads along x
+        ([allv[::-1], allv[1:17] + [0]], 0),                    # ... and x is its stride-1 axis
+        ([allv[:17], allv[::-1], allv[5:]], 2),                 # K=3: two riders with different micro-tiles
+        ([allv[::-1], [17, 4, 11]], None),                      # a small table whose fastest axis is not the output's
+    ]
+    try:
+        for scopes, elim in cases:
+            ofs, dfs = [], []
+            for sc in scopes:
+                o, d = rand_factor(ctx, rng, sc, cards)
+                ofs.append(o); dfs.append(d)
+            out_scope = [v for v in allv if v != elim]
+            want = orc.product_sum_out(ofs, out_scope, elim, cards)
+            for tma, rider in ((1, 1), (1, 0), (0, 0)):     # tile by TMA bulk copies (other operands prefetched or not) / cp.async
+                capi.tuning_set("staged_tma", tma)
+                capi.tuning_set("staged_async", rider)
+                got = fused_product_sum_out(ctx, dfs, out_scope, elim)
+                seen.add(ctx.last_launch()[0].split(",")[0])
+                assert np.array_equal(got.values(), want.values), (scopes, elim, tma, rider, ctx.last_launch())
+                assert zclose(got.partition, want.partition)
+    finally:
+        capi.tuning_set("staged_tma", 1)
+        capi.tuning_set("staged_async", 1)
+    # LDGSTS tiles, the transposed operand alone by TMA, and other operands riding along
+    variants = {s.split("<")[1] for s in seen}
+    assert any(v.startswith("staged") for v in variants), variants
+    assert any(v.startswith("tma/") and len(v) == 5 for v in variants), variants
+    assert any(v.startswith("tma/") and len(v) >= 6 for v in variants), variants
 
 
 def test_bcast_2p30_partition_invariant(ctx):
