@@ -486,16 +486,16 @@ __global__ void __launch_bounds__(kBlock, 2) contract_staged(const __grid_consta
     const uint32_t n_chunks = (uint32_t)(h.n_items / CH);
     double zacc = 0.0;
     // the chunk's base offsets are the same for the whole CTA and, for a transposed operand, a sum over two dozen
-    // one-bit fields: thread k computes operand k's (thread K the output's) one chunk ahead, the CTA reads them
-    // after the barrier that ends the previous chunk
+    // one-bit fields: computed one chunk ahead, the CTA reads them after the barrier that ends the previous chunk
     __shared__ uint32_t s_hi[2][kMaxK + 1];
+    // warp w <= K owns operand w (warp K the output), lane f its bit-field f: one warp-wide integer add per chunk
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    Field mine = Field{0u, 0u, 0u};
+    if (warp <= (uint32_t)K && lane < p.nf[warp]) mine = p.f[warp][lane];
     auto chunk_base = [&](uint32_t c, uint32_t *dst) {
-        const uint32_t who = threadIdx.x;
-        if (who <= (uint32_t)K) {
-            uint32_t o = 0;
-            const uint32_t item = c * CH;
-            for (int f = 0; f < (int)p.nf[who]; ++f) o += ((item >> p.f[who][f].sh) & p.f[who][f].mask) * p.f[who][f].mul;
-            dst[who] = o;
+        if (warp <= (uint32_t)K) {
+            const uint32_t o = __reduce_add_sync(0xffffffffu, (((c * CH) >> mine.sh) & mine.mask) * mine.mul);
+            if (lane == 0) dst[warp] = o;
         }
     };
     if (blockIdx.x < n_chunks) chunk_base(blockIdx.x, s_hi[0]);
@@ -937,7 +937,7 @@ static uint64_t resident_ctas_dyn(bnpp_ctx *ctx, F fn, unsigned smem)
     static std::map<std::pair<int, const void *>, bool> granted;
     const void *f = reinterpret_cast<const void *>(fn);
     if (!granted[{ctx->device, f}]) {
-        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226u * 1024u)) != cudaSuccess) return 0;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmemBudget) != cudaSuccess) return 0;
         granted[{ctx->device, f}] = true;
     }
     const auto key = std::make_tuple(ctx->device, f, (smem + 1023u) / 1024u);
@@ -1444,20 +1444,13 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
                 memset(&t, 0, sizeof t);
                 t.tile = st.tile;
                 t.rbits = rb;
-                // run positions: the run bits the lanes drive lowest (in the operand's own order), then the others
+                // run positions: the run bits the lanes drive lowest, in lane order (measured: 70-76% of peak on the
+                // reversed F-bcast shapes against 50-67% in stride order), then the others
                 t.nrb = (uint8_t)(ilog2(st.tile) - rb);
                 bool placed[12] = {false};
                 int next = 0;
-                static const int order = [] { const char *e = getenv("BNPP_TMA_RUNORDER"); return e ? atoi(e) : 1; }();
-                if (order == 1) {
-                    for (int i = 0; i < 5; ++i)
-                        if (lane_rank[i] >= (int)rb) { t.rpos[lane_rank[i] - rb] = (uint8_t)next++; placed[lane_rank[i] - rb] = true; }
-                } else if (order == 2) {
-                    for (int i = 0; i < 5; ++i)
-                        if (lane_rank[i] >= (int)rb) placed[lane_rank[i] - rb] = true;
-                    for (int i = 0; i < (int)t.nrb; ++i)
-                        if (placed[i]) t.rpos[i] = (uint8_t)next++;
-                }
+                for (int i = 0; i < 5; ++i)
+                    if (lane_rank[i] >= (int)rb) { t.rpos[lane_rank[i] - rb] = (uint8_t)next++; placed[lane_rank[i] - rb] = true; }
                 for (int i = 0; i < (int)t.nrb; ++i)
                     if (!placed[i]) t.rpos[i] = (uint8_t)next++;
                 const uint32_t pitch = (1u << rb) + 2u;
@@ -1482,7 +1475,7 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
             ParamsP2T &pt = desc->p2t;
             if (ok && staged_tma_enabled() && k <= kTmaMaxK && tma_operand(st, even, pt.t[staged])) {
                 pt.mask = 1u << staged;
-                static const uint32_t budget = [] { const char *e = getenv("BNPP_STAGED_BUDGET_KB"); return e ? (uint32_t)atoi(e) * 1024u : kStagedSmemBudget; }();
+                const uint32_t budget = kStagedSmemBudget;
                 auto padded = [](const TmaOperand &t) { return t.tile + 2u * (t.tile >> t.rbits); };
                 uint32_t doubles = padded(pt.t[staged]);
                 // the other operands ride along while two stages of everything fit, smallest tile first
@@ -1511,8 +1504,16 @@ int contract_plan(bnpp_ctx *ctx, int k, const bnpp_operand *ops, const bnpp_scop
                     }
                 pt.stage_doubles = off;
                 pt.stages = (3u * off * 8u <= budget) ? 3u : 2u;
+                // An operand that carries an eighth of the traffic and does NOT fit the ring would be loaded chunk by chunk
+                // into registers: there the element-wise kernel below is the faster one (F-elem reversed: 89-92% of peak
+                // against 82-83%), and this one wins when everything big is prefetched (F-bcast reversed: 70-80% against 61-66%)
+                uint64_t total_bytes = 8 * n_out;
+                for (int q = 0; q < k; ++q) total_bytes += op_bytes[q];
+                bool all_big = true;
+                for (int q = 0; q < k; ++q)
+                    if (!((pt.mask >> q) & 1u) && op_bytes[q] * 8 >= total_bytes) all_big = false;
                 tma_fn fn = pick_staged_tma(k, C);
-                if (fn && 2u * off * 8u <= budget) {
+                if (fn && all_big && 2u * off * 8u <= budget) {
                     pt.b = p;
                     desc->p2 = true;
                     desc->tma = true;
