@@ -103,15 +103,16 @@ __device__ __forceinline__ void mvt_produce(const ParamsMVT &p, uint32_t t, uint
 
 // A row of 2 * P doubles per thread at a pitch of 2 * P doubles puts the 8 lanes of a 128-bit shared load on 8 / P
 // distinct 16-byte columns (P = 2: 2-way, P = 4: 4-way bank conflicts).  Reading the pairs of a row in an order ROTATED
-// by R -- R differs between the lanes that would collide -- removes the conflicts; the products land in registers by
-// their own index, so the sum still runs over x = 0, 1, ... in the reference's order.
-template <int K, int P, int R>
-__device__ __forceinline__ double row_sum_rot(const double *const (&row)[K])
+// by r -- r differs between the lanes that would collide -- removes the conflicts.
+template <int K, int P>
+__device__ __forceinline__ double row_sum_rot(const double *const (&row)[K], uint32_t r)
 {
-    double pr[2 * P];
+    // lane-dependent ADDRESSES, one instruction stream: a switch over the rotation would run its cases one after the
+    // other with a quarter of the lanes each, and give back the wavefronts the rotation saves
+    double2 pr[P];      // pr[i]: the products of pair (i + r) mod P
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-        const int pi = (i + R) % P;
+        const uint32_t pi = (i + r) & (P - 1);
         double2 a = *reinterpret_cast<const double2 *>(row[0] + 2 * pi);
 #pragma unroll
         for (int k = 1; k < K; ++k) {
@@ -119,12 +120,28 @@ __device__ __forceinline__ double row_sum_rot(const double *const (&row)[K])
             a.x = __dmul_rn(a.x, b.x);
             a.y = __dmul_rn(a.y, b.y);
         }
-        pr[2 * pi] = a.x;
-        pr[2 * pi + 1] = a.y;
+        pr[i] = a;
+    }
+    // back into index order with selects (a barrel rotation by r), so the sum runs over x = 0, 1, ... like the reference's
+#pragma unroll
+    for (int b = 1; b < P; b <<= 1) {
+        const bool on = (r & b) != 0;
+        double2 t[P];
+#pragma unroll
+        for (int s = 0; s < P; ++s) {
+            const double2 moved = pr[(s + P - b) % P];
+            t[s].x = on ? moved.x : pr[s].x;
+            t[s].y = on ? moved.y : pr[s].y;
+        }
+#pragma unroll
+        for (int s = 0; s < P; ++s) pr[s] = t[s];
     }
     double acc = 0.0;
 #pragma unroll
-    for (int x = 0; x < 2 * P; ++x) acc = __dadd_rn(acc, pr[x]);
+    for (int s = 0; s < P; ++s) {
+        acc = __dadd_rn(acc, pr[s].x);
+        acc = __dadd_rn(acc, pr[s].y);
+    }
     return acc;
 }
 
@@ -168,15 +185,9 @@ __global__ void __launch_bounds__(kBlock) contract_mvt(const __grid_constant__ P
             for (int k = 0; k < K; ++k) row[k] = stage + p.soff[k] + (rowtab[j * K + k] + s_meta[s][k]);
             double acc = 0.0;
             if (MODE == 2 && cx == 8) {
-                switch ((j >> 1) & 3u) {
-                case 0: acc = row_sum_rot<K, 4, 0>(row); break;
-                case 1: acc = row_sum_rot<K, 4, 1>(row); break;
-                case 2: acc = row_sum_rot<K, 4, 2>(row); break;
-                default: acc = row_sum_rot<K, 4, 3>(row); break;
-                }
+                acc = row_sum_rot<K, 4>(row, (j >> 1) & 3u);
             } else if (MODE == 2 && cx == 4) {
-                if ((j >> 2) & 1u) acc = row_sum_rot<K, 2, 1>(row);
-                else acc = row_sum_rot<K, 2, 0>(row);
+                acc = row_sum_rot<K, 2>(row, (j >> 2) & 1u);
             } else if (MODE == 2) {
 #pragma unroll 2
                 for (uint32_t x = 0; x < cx; x += 2) {
