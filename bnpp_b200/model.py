@@ -238,6 +238,7 @@ class BN:
         self._plans = {}
         self._shard_cache = {}
         self._batch_plans = {}
+        self._order_cache = {}      # (observed ids, heuristic) -> elimination order: a function of the model's structure only
         self._res2 = None
         self._batch_out = {}
         self.last_timing = {}
@@ -319,10 +320,16 @@ class BN:
         evidence = dict(evidence or {})
         if comm is not None and comm.world > 1:
             evidence, _ = self.shard(evidence, heuristic, comm)
-        variables = [v for v in range(self.nvars) if v not in evidence]
-        order, _ = self.order(variables, evidence, heuristic)
-        t1 = time.perf_counter()
         observed = sorted(evidence)
+        okey = (tuple(observed), heuristic)
+        order = self._order_cache.get(okey)
+        if order is None:
+            variables = [v for v in range(self.nvars) if v not in evidence]
+            order, _ = self.order(variables, evidence, heuristic)
+            if len(self._order_cache) >= self.MAX_PLANS:
+                self._order_cache.pop(next(iter(self._order_cache)))
+            self._order_cache[okey] = order
+        t1 = time.perf_counter()
         p = self.plan(observed, order)
         t2 = time.perf_counter()
         if self._res2 is None:
@@ -458,6 +465,7 @@ class BN:
             p.close()
         self._plans = {}
         self._batch_plans = {}
+        self._order_cache = {}
 
     def close(self):
         self.drop_plans()
