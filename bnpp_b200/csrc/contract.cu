@@ -28,6 +28,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <tuple>
 #include <vector>
 
@@ -919,6 +920,8 @@ template <class F>
 static uint64_t resident_ctas(bnpp_ctx *ctx, F fn)
 {
     static std::map<std::pair<int, const void *>, int> cache;      // per device and variant
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     const auto key = std::make_pair(ctx->device, reinterpret_cast<const void *>(fn));
     auto it = cache.find(key);
     if (it == cache.end()) {
@@ -935,6 +938,8 @@ static uint64_t resident_ctas_dyn(bnpp_ctx *ctx, F fn, unsigned smem)
 {
     static std::map<std::tuple<int, const void *, unsigned>, int> cache;       // per device, variant and KB of shared memory
     static std::map<std::pair<int, const void *>, bool> granted;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
     const void *f = reinterpret_cast<const void *>(fn);
     if (!granted[{ctx->device, f}]) {
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStagedSmemBudget) != cudaSuccess) return 0;

@@ -20,6 +20,7 @@
 // -- so a result is bit-identical to the launch-per-bucket paths.
 #include <cstdlib>
 #include <map>
+#include <mutex>
 
 #include "common.cuh"
 #include "fused.hpp"
@@ -323,11 +324,15 @@ int fused_launch(bnpp_ctx *ctx, int G, const FusedLaunch &p)
     }
     if (p.arena & 1u) return fail(ctx, BNPP_EINVAL, "fused VE: the arena of a set must be an even number of doubles");
     const size_t smem = fused_smem_bytes(G, p.arena);
-    static std::map<std::pair<int, const void *>, size_t> granted;      // dynamic shared memory opted into, per device and variant
-    size_t &have = granted[{ctx->device, reinterpret_cast<const void *>(fn)}];
-    if (smem > have) {
-        BNPP_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        have = smem;
+    {
+        static std::map<std::pair<int, const void *>, size_t> granted;      // dynamic shared memory opted into, per device and variant
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        size_t &have = granted[{ctx->device, reinterpret_cast<const void *>(fn)}];
+        if (smem > have) {
+            BNPP_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            have = smem;
+        }
     }
     int per_sm = 0;
     BNPP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kFusedThreads, smem));
@@ -360,11 +365,15 @@ const void *tasks_kernel() { return reinterpret_cast<const void *>(ve_tasks); }
 int tasks_geometry(bnpp_ctx *ctx, uint32_t n_tasks, uint32_t arena, unsigned *grid, unsigned *smem)
 {
     const size_t bytes = fused_smem_bytes(128, arena);
-    static std::map<std::pair<int, const void *>, size_t> granted;
-    size_t &have = granted[{ctx->device, tasks_kernel()}];
-    if (bytes > have) {
-        BNPP_CUDA(ctx, cudaFuncSetAttribute(ve_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        have = bytes;
+    {
+        static std::map<std::pair<int, const void *>, size_t> granted;
+        static std::mutex mu;
+        std::lock_guard<std::mutex> lock(mu);
+        size_t &have = granted[{ctx->device, tasks_kernel()}];
+        if (bytes > have) {
+            BNPP_CUDA(ctx, cudaFuncSetAttribute(ve_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            have = bytes;
+        }
     }
     int per_sm = 0;
     BNPP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ve_tasks, kFusedThreads, bytes));
