@@ -681,7 +681,7 @@ def main():
         tj = json.load(open(tp))      # dram__bytes_read.sum + dram__bytes_write.sum of this launch, one `ncu --set full` capture
         if tj.get("kernel_variant") and tj["kernel_variant"] in wl.get("kernel", "") and tj.get("algorithmic_bytes") == wl["bytes"]:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-            traffic_src = "profiles/r2_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of the same launch: same kernel variant, same algorithmic bytes; profiles/r2_launches.csv)"
+            traffic_src = "profiles/r2_traffic.json (one ncu --set full capture of the same launch, profiles/r2_canon_full.md: same kernel variant, same algorithmic bytes)"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": wl["bytes"], "peak_kind": peak_kind,
                 "measured_in": "second timed pass of the same K steps with a CUDA event pair around every launch "
