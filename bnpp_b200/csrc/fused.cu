@@ -169,58 +169,81 @@ __device__ __forceinline__ double entries_dispatch(const SetView<SPW> &v, const 
     return entries_any<K, G, SPW>(v, op, amask, tab, n_out, cx, lane, d);
 }
 
-// the steps of one program for one evidence set (b), on the G lanes that own it
+// the steps of one program for one evidence set (b), on the G lanes that own it.
+// Decoding a step costs no memory round trip: the record of a step (header, operand records, observed axes -- the same
+// words for every lane of the warp) is fetched with ONE coalesced load, lane i word i, while the PREVIOUS step runs, and
+// read field by field with warp shuffles; the evidence values of the set sit in registers the same way (lane l of the
+// set holds values 4l .. 4l+3).  Records longer than 32 words and plans with more than 32 observed variables read the
+// rest from memory.  `prog` must be readable 32 words past the last record.
 template <int G, int SPW>
 __device__ __forceinline__ void run_steps(const uint32_t *__restrict__ prog, const uint32_t *__restrict__ offtab, uint32_t n_steps,
-                                          const uint8_t *ev, double *result, double *zout, uint32_t nb, uint32_t b, bool live,
-                                          const SetView<SPW> &v, uint32_t lane, double *s_red)
+                                          const uint8_t *ev, uint32_t n_obs, double *result, double *zout, uint32_t nb, uint32_t b,
+                                          bool live, const SetView<SPW> &v, uint32_t lane, double *s_red)
 {
     const uint32_t tw = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t pc = 0;
+    constexpr uint32_t kEvLanes = G < 8 ? G : 8;                // lanes of a set inside one warp that hold evidence values
+    const bool ev_regs = n_obs <= 4u * kEvLanes;
+    const uint32_t l = (G < 32) ? lane : tw;                    // G = 128: every warp keeps its own copy
+    uint32_t evw = 0;
+    if (ev_regs && l < kEvLanes) {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            if (4u * l + j < n_obs) evw |= (uint32_t)ev[4u * l + j] << (8u * j);
+    }
+    const uint32_t my_set = (G < 32) ? tw % SPW : 0u;
+    auto evidence = [&](uint32_t i) -> uint32_t {
+        if (ev_regs) return (__shfl_sync(0xffffffffu, evw, (i >> 2) * SPW + my_set) >> (8u * (i & 3u))) & 0xffu;
+        return ev[i];
+    };
+    uint32_t rec0 = 0;                      // first word of the current step's record
+    uint32_t w = __ldg(prog + tw);
     for (uint32_t s = 0; s < n_steps; ++s) {
-        const uint4 h0 = ldg4(prog + pc), h1 = ldg4(prog + pc + 4);
-        pc += kFusedHeaderWords;
-        const uint32_t n_out = h0.x, cx = h0.y, k = h0.z & 0xffu, flags = h0.z >> 8, tab_off = h1.x;
+        auto word = [&](uint32_t i) -> uint32_t { return i < 32u ? __shfl_sync(0xffffffffu, w, i) : __ldg(prog + rec0 + i); };
+        const uint32_t n_out = word(0), cx = word(1), kf = word(2), k = kf & 0xffu, flags = kf >> 8, tab_off = word(4);
         Dest d;
-        d.out_off = h0.w;
+        d.out_off = word(3);
         d.store = live;
         if (flags & kFusedToResult) {
-            d.result = result + ((uint64_t)h0.w * nb + b);
+            d.result = result + ((uint64_t)d.out_off * nb + b);
             d.stride = nb;
         } else if (flags & kFusedToGlobal) {      // single queries inside a launch-per-bucket plan: a later launch reads it
-            d.result = reinterpret_cast<double *>(((uint64_t)h1.z << 32) | (uint64_t)h1.y);
+            d.result = reinterpret_cast<double *>(((uint64_t)word(6) << 32) | (uint64_t)word(5));
             d.stride = 1;
         } else {
             d.result = nullptr;
             d.stride = 0;
         }
         // operand records (the k of a step is uniform over its lanes)
+        uint32_t at = kFusedHeaderWords;
         Operands op;
         uint32_t amask = 0;
 #pragma unroll
         for (int q = 0; q < kMaxK; ++q) {
             if (q < (int)k) {
-                const uint4 r = ldg4(prog + pc);
-                pc += kFusedOperandWords;
-                op.sx[q] = r.z;
-                if ((r.x & 0xffu) == 0) {
-                    op.base[q] = r.y;
+                const uint32_t r0 = word(at), r1 = word(at + 1), r2 = word(at + 2);
+                op.sx[q] = r2;
+                if ((r0 & 0xffu) == 0) {
+                    at += kFusedOperandWords;
+                    op.base[q] = r1;
                     op.cpt[q] = nullptr;
                     amask |= 1u << q;
                 } else {
-                    const uint32_t nobs = r.x >> 8;
+                    const uint32_t r3 = word(at + 3);
+                    at += kFusedOperandWords;
+                    const uint32_t nobs = r0 >> 8;
                     uint32_t e = 0;
                     for (uint32_t j = 0; j < nobs; j += 2) {
-                        const uint4 ob = ldg4(prog + pc);
-                        pc += 4;
-                        e += ob.x * ev[ob.y];
-                        if (j + 1 < nobs) e += ob.z * ev[ob.w];
+                        e += word(at) * evidence(word(at + 1));
+                        if (j + 1 < nobs) e += word(at + 2) * evidence(word(at + 3));
+                        at += 4;
                     }
                     op.base[q] = 0;
-                    op.cpt[q] = reinterpret_cast<const double *>(((uint64_t)r.w << 32) | (uint64_t)r.y) + e;
+                    op.cpt[q] = reinterpret_cast<const double *>(((uint64_t)r3 << 32) | (uint64_t)r1) + e;
                 }
             }
         }
+        rec0 += at;
+        const uint32_t w_next = __ldg(prog + rec0 + tw);       // the next step's record, on its way while this step runs
         const uint32_t *tab = offtab + tab_off;
         const bool pairs = (flags & kFusedPairs) != 0;
         double zacc;
@@ -249,6 +272,7 @@ __device__ __forceinline__ void run_steps(const uint32_t *__restrict__ prog, con
             if (lane == 0 && live) zout[b] = z;
         }
         group_sync<G>();     // the step's output is complete, and its operands are dead, before the next step
+        w = w_next;
     }
 }
 
@@ -280,7 +304,7 @@ __global__ void __launch_bounds__(kFusedThreads) ve_fused(const __grid_constant_
         const bool live = b < p.nb;      // lanes of a missing set repeat the last one (they take part in the syncs), stores off
         if (!live) b = p.nb - 1;
         const uint8_t *ev = p.ev ? p.ev + (uint64_t)b * p.n_obs : p.ev_inline;
-        run_steps<G, SPW>(p.prog, p.offtab, p.n_steps, ev, p.result, p.z, p.nb, b, live, v, lane, s_red);
+        run_steps<G, SPW>(p.prog, p.offtab, p.n_steps, ev, p.n_obs, p.result, p.z, p.nb, b, live, v, lane, s_red);
     }
 }
 
@@ -295,7 +319,7 @@ __global__ void __launch_bounds__(kFusedThreads) ve_tasks(const __grid_constant_
     v.wbase = 0;
     for (uint32_t t = blockIdx.x; t < p.n_tasks; t += gridDim.x) {
         const uint4 task = ldg4(reinterpret_cast<const uint32_t *>(p.tasks + t));      // prog offset, offtab base, steps, arena
-        run_steps<128, 1>(p.prog + task.x, p.offtab + task.y, task.z, p.ev_inline, p.result, p.z, 1u, 0u, true, v, threadIdx.x, s_red);
+        run_steps<128, 1>(p.prog + task.x, p.offtab + task.y, task.z, p.ev_inline, p.n_obs, p.result, p.z, 1u, 0u, true, v, threadIdx.x, s_red);
         __syncthreads();
     }
 }

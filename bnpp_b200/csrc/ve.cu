@@ -1049,7 +1049,7 @@ int upload_tasks(bnpp_ve_plan *pl, const double *const *tables_dev)
     }
     if (!pl->tasks_prog_dev) {
         double *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
-        int rc = bnpp_alloc(ctx, pl->tasks_prog.size() / 2 + 2, &p0);
+        int rc = bnpp_alloc(ctx, pl->tasks_prog.size() / 2 + 18, &p0);      // the kernel prefetches 32 words past a record
         if (rc == BNPP_OK) rc = bnpp_alloc(ctx, pl->tasks_tab.size() / 2 + 2, &p1);
         if (rc == BNPP_OK) rc = bnpp_alloc(ctx, pl->tasks_rec.size() * 2 + 2, &p2);
         if (rc != BNPP_OK) return rc;
@@ -1108,7 +1108,7 @@ int run_fused(bnpp_ve_plan *pl, FusedProgram &fp, int G, const double *const *ta
         }
         if (!fp.prog_dev) {
             double *store = nullptr;
-            const int rc = bnpp_alloc(ctx, fp.prog.size() / 2 + 2, &store);
+            const int rc = bnpp_alloc(ctx, fp.prog.size() / 2 + 18, &store);      // the kernel prefetches 32 words past a record
             if (rc != BNPP_OK) return rc;
             fp.prog_dev = reinterpret_cast<uint32_t *>(store);
         }
