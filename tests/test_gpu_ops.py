@@ -279,6 +279,50 @@ def test_transposed_operands_through_shared_memory(ctx):
     assert any(v.startswith("tma/") and len(v) >= 6 for v in variants), variants
 
 
+def test_transposed_operands_many_chunks_per_cta(ctx):
+    """the staged kernels as persistent loops: 2^22 output entries = 2048 chunks over ~300 CTAs, so every CTA walks
+    several chunks -- the stage ring wraps, the mbarrier parities flip, the chunk bases of later chunks are used -- in
+    the TMA variant with the other operand riding along (F-bcast shape: B reversed and without x0, A without the
+    innermost axis), with the transposed operand alone, and in the element-wise variant; entry-wise against the oracle"""
+    from bnpp_b200 import capi
+    from bnpp_b200.factor import fused_product_sum_out
+    rng = random.Random(33)
+    nbits = 23
+    cards = [2] * nbits
+    allv = list(range(nbits))
+    cases = [
+        ([allv[:-1], allv[1:][::-1]], 0),                       # F-bcast, leading variable summed out
+        ([allv[:-1], allv[1:][::-1]], 11),                      # ... a middle one (both operands hold it)
+        ([allv[:-1], allv[1:][::-1]], nbits - 1),               # ... the trailing one
+        ([allv, allv[::-1]], 11),                               # F-elem reversed
+        ([allv[::-1]], None),                                   # K = 1: a full bit-reversal copy
+    ]
+    seen = set()
+    try:
+        for scopes, elim in cases:
+            ofs, dfs = [], []
+            for sc in scopes:
+                o, d = rand_factor(ctx, rng, sc, cards)
+                ofs.append(o); dfs.append(d)
+            out_scope = [v for v in allv if v != elim]
+            want = orc.product_sum_out(ofs, out_scope, elim, cards)
+            for tma, rider in ((1, 1), (1, 0), (0, 0)):
+                capi.tuning_set("staged_tma", tma)
+                capi.tuning_set("staged_async", rider)
+                got = fused_product_sum_out(ctx, dfs, out_scope, elim)
+                name, grid, _ = ctx.last_launch()
+                seen.add(name.split(",")[0].split("<")[1])
+                assert grid * 2 < (1 << (len(out_scope) - 1)) // 1024, (name, grid)        # more than two chunks per CTA
+                assert np.array_equal(got.values(), want.values), (scopes, elim, tma, rider, name)
+                assert zclose(got.partition, want.partition)
+                del got
+            del ofs, dfs, want
+    finally:
+        capi.tuning_set("staged_tma", 1)
+        capi.tuning_set("staged_async", 1)
+    assert any(v.startswith("staged") for v in seen) and any(v.startswith("tma/") and len(v) >= 6 for v in seen), seen
+
+
 def test_bcast_2p30_partition_invariant(ctx):
     """largest single-GPU shapes: 2^30 union entries (4 GiB operands); Z(sum_out) must not depend on
     which variable is summed out, and must equal the direct reduction of a product slice"""
