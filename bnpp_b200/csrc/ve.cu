@@ -562,6 +562,13 @@ void fused_build(bnpp_ve_plan *pl)
 // segment = true: a run of steps inside a launch-per-bucket plan -- intermediates made by earlier launches are read
 // from the plan's global arena (operand kind 1 without observed axes), an output that a LATER launch reads is
 // written there (kFusedToGlobal); only intermediates born and consumed inside the run live in shared memory.
+// BNPP_FUSED_STACK=0: first-fit arenas only (tests run both layouts)
+static bool fused_stack_arena()
+{
+    const char *e = getenv("BNPP_FUSED_STACK");
+    return !(e && e[0] == '0');
+}
+
 void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment, FusedProgram &fp)
 {
     fp.built = true;
@@ -636,6 +643,60 @@ void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment,
             give(aoff[id], pl->f[id].size);
         }
         if (st.out >= 0 && in_smem[st.out] && last_use[st.out] < 0) give(aoff[st.out], pl->f[st.out].size);   // never read
+    }
+    // When the steps form a forest (every shared-memory intermediate read by exactly one step) and `order` is a
+    // post-order walk of it, a TWO-ENDED STACK lays the arena out without the holes of first fit: the result of a step
+    // goes to the end opposite to its operands' (which are the top of their end: popped as soon as the step is done).
+    // The peak is the live set of the walk itself (config 5: 192 doubles where first fit needs 240) -- the arena of a
+    // set is what bounds the evidence sets resident on an SM.
+    {
+        std::vector<int> reads(pl->f.size(), 0), side(pl->f.size(), 0);
+        bool forest = true;
+        for (size_t i = 0; i < ns && forest; ++i) {
+            std::vector<int> seen;
+            for (int id : pl->steps[order[i]].operands) {
+                if (pl->f[id].src >= 0 || !in_smem[id] || std::find(seen.begin(), seen.end(), id) != seen.end()) continue;
+                seen.push_back(id);
+                if (++reads[id] > 1) forest = false;
+            }
+        }
+        // sides top down: an output sits opposite to the outputs of the steps it feeds on
+        for (size_t i = ns; i-- > 0 && forest;) {
+            const PlanStep &st = pl->steps[order[i]];
+            const int mine = (st.out >= 0 && in_smem[st.out]) ? side[st.out] : 0;
+            for (int id : st.operands)
+                if (pl->f[id].src < 0 && in_smem[id]) side[id] = 1 - mine;
+        }
+        std::vector<uint64_t> at(pl->f.size(), 0);      // distance of the table's START (side 0) / END (side 1) from its end of the arena
+        uint64_t tops[2] = {0, 0}, best = 0;
+        for (size_t i = 0; i < ns && forest; ++i) {
+            const PlanStep &st = pl->steps[order[i]];
+            if (st.out >= 0 && in_smem[st.out]) {
+                const uint64_t n = (pl->f[st.out].size + 1) & ~1ull;
+                const int sd = side[st.out];
+                at[st.out] = sd == 0 ? tops[0] : tops[1] + n;
+                tops[sd] += n;
+                best = std::max(best, tops[0] + tops[1]);
+            }
+            std::vector<int> seen;
+            for (int id : st.operands) {
+                if (pl->f[id].src >= 0 || !in_smem[id] || std::find(seen.begin(), seen.end(), id) != seen.end()) continue;
+                seen.push_back(id);
+                tops[side[id]] -= (pl->f[id].size + 1) & ~1ull;
+            }
+            // popped tables must have been the top of their end: whatever is left starts below them
+            for (int id : seen) {
+                const uint64_t n = (pl->f[id].size + 1) & ~1ull;
+                const uint64_t start = side[id] == 0 ? at[id] : at[id] - n;
+                if (start < tops[side[id]]) forest = false;
+            }
+            if (st.out >= 0 && in_smem[st.out] && last_use[st.out] < 0) tops[side[st.out]] -= (pl->f[st.out].size + 1) & ~1ull;
+        }
+        if (forest && best > 0 && best < peak && fused_stack_arena()) {
+            for (size_t id = 0; id < pl->f.size(); ++id)
+                if (in_smem[id]) aoff[id] = side[id] == 0 ? at[id] : best - at[id];
+            peak = best;
+        }
     }
     if (peak >= (1ull << 24)) return;
 
