@@ -57,7 +57,8 @@ def _time_launch(ctx, fn, iters):
         e1.synchronize()
         if it >= 2:
             times.append(e0.elapsed_time(e1))
-    return sum(times) / len(times)
+    times.sort()
+    return times[len(times) // 2]      # the median: one hiccup (a clock sample, a page fault) must not carry a row
 
 
 def run_mv(ctx, cards_list, iters=5, verbose=True, peak=None, how=""):
