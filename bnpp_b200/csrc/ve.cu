@@ -493,7 +493,17 @@ bool fused_default_on()
 // at any time -- the arena of one evidence set has to fit in shared memory many times over.
 // Any topological order gives the same numbers: operand lists, hence the order of the
 // multiplications inside a bucket, are untouched.
-void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment, FusedProgram &fp);
+// Scratch of fused_encode, sized by the PLAN (steps, factors) and built once per thread: a plan of a thousand buckets is
+// cut into a few hundred tasks, and a task must cost what ITS steps cost, not a pass over the plan.  Everything a call
+// marks is put back before it returns.
+struct EncodeScratch {
+    std::vector<int> pos, last_use, producer, reads, side;
+    std::vector<char> in_smem, read_inside, read_outside;
+    std::vector<uint64_t> aoff, at;
+    std::vector<int> cons_off, cons;        // consumers[f] = steps that read factor f (CSR)
+    explicit EncodeScratch(const bnpp_ve_plan *pl);
+};
+void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment, FusedProgram &fp, EncodeScratch *scratch = nullptr);
 
 void fused_build(bnpp_ve_plan *pl)
 {
@@ -569,21 +579,64 @@ static bool fused_stack_arena()
     return !(e && e[0] == '0');
 }
 
-void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment, FusedProgram &fp)
+EncodeScratch::EncodeScratch(const bnpp_ve_plan *pl)
+    : pos(pl->steps.size(), -1), last_use(pl->f.size(), -1), producer(pl->f.size(), -1), reads(pl->f.size(), 0), side(pl->f.size(), 0),
+      in_smem(pl->f.size(), 0), read_inside(pl->f.size(), 0), read_outside(pl->f.size(), 0), aoff(pl->f.size(), 0), at(pl->f.size(), 0),
+      cons_off(pl->f.size() + 1, 0)
+{
+    const size_t all = pl->steps.size();
+    for (size_t s = 0; s < all; ++s) {
+        if (pl->steps[s].out >= 0) producer[pl->steps[s].out] = (int)s;
+        for (int id : pl->steps[s].operands)
+            if (pl->f[id].src < 0) ++cons_off[id + 1];
+    }
+    for (size_t i = 0; i < pl->f.size(); ++i) cons_off[i + 1] += cons_off[i];
+    cons.resize(cons_off.back());
+    std::vector<int> fill(cons_off.begin(), cons_off.end() - 1);
+    for (size_t s = 0; s < all; ++s)
+        for (int id : pl->steps[s].operands)
+            if (pl->f[id].src < 0) cons[fill[id]++] = (int)s;
+}
+
+void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment, FusedProgram &fp, EncodeScratch *scratch)
 {
     fp.built = true;
     fp.ok = false;
-    const size_t ns = order.size(), all = pl->steps.size();
+    const size_t ns = order.size();
     if (ns == 0) return;
-    std::vector<int> pos(all, -1), last_use(pl->f.size(), -1), producer(pl->f.size(), -1);
+    std::unique_ptr<EncodeScratch> own;
+    if (!scratch) {
+        own.reset(new EncodeScratch(pl));
+        scratch = own.get();
+    }
+    std::vector<int> &pos = scratch->pos, &last_use = scratch->last_use, &producer = scratch->producer;
+    std::vector<char> &in_smem = scratch->in_smem, &read_inside = scratch->read_inside, &read_outside = scratch->read_outside;
+    std::vector<uint64_t> &aoff = scratch->aoff;
+    // whatever this call marks (its steps, the intermediates they make) goes back to the initial state on every way out
+    struct Reset {
+        EncodeScratch *sc;
+        const bnpp_ve_plan *pl;
+        const std::vector<int> &order;
+        ~Reset()
+        {
+            for (int st : order) {
+                sc->pos[st] = -1;
+                const int id = pl->steps[st].out;
+                if (id < 0) continue;
+                sc->last_use[id] = -1;
+                sc->reads[id] = sc->side[id] = 0;
+                sc->in_smem[id] = sc->read_inside[id] = sc->read_outside[id] = 0;
+                sc->aoff[id] = sc->at[id] = 0;
+            }
+        }
+    } reset{scratch, pl, order};
     for (size_t i = 0; i < ns; ++i) pos[order[i]] = (int)i;
-    for (size_t s = 0; s < all; ++s)
-        if (pl->steps[s].out >= 0) producer[pl->steps[s].out] = (int)s;
     // an intermediate lives in shared memory iff it is made here; then every reader must be here too
-    std::vector<char> in_smem(pl->f.size(), 0), read_inside(pl->f.size(), 0), read_outside(pl->f.size(), 0);
-    for (size_t s = 0; s < all; ++s)
-        for (int id : pl->steps[s].operands) {
-            if (pl->f[id].src >= 0) continue;
+    for (size_t i = 0; i < ns; ++i) {
+        const int id = pl->steps[order[i]].out;
+        if (id < 0 || pl->f[id].src >= 0) continue;
+        for (int c = scratch->cons_off[id]; c < scratch->cons_off[id + 1]; ++c) {
+            const int s = scratch->cons[c];
             if (pos[s] >= 0) {
                 read_inside[id] = 1;
                 last_use[id] = std::max(last_use[id], pos[s]);
@@ -591,14 +644,11 @@ void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment,
                 read_outside[id] = 1;
             }
         }
-    for (size_t i = 0; i < pl->f.size(); ++i) {
-        if (pl->f[i].src >= 0 || producer[i] < 0 || pos[producer[i]] < 0) continue;
-        if (!segment) in_smem[i] = 1;
-        else if (read_inside[i] && read_outside[i]) return;       // two homes: not a run this builder takes
-        else in_smem[i] = read_inside[i];
+        if (!segment) in_smem[id] = 1;
+        else if (read_inside[id] && read_outside[id]) return;       // two homes: not a run this builder takes
+        else in_smem[id] = read_inside[id];
     }
     // arena of one evidence set: first fit over the order, in doubles
-    std::vector<uint64_t> aoff(pl->f.size(), 0);
     std::vector<std::pair<uint64_t, uint64_t>> free_list;   // (offset, size)
     uint64_t top = 0, peak = 0;
     auto take = [&](uint64_t n) {
@@ -650,7 +700,7 @@ void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment,
     // The peak is the live set of the walk itself (config 5: 192 doubles where first fit needs 240) -- the arena of a
     // set is what bounds the evidence sets resident on an SM.
     {
-        std::vector<int> reads(pl->f.size(), 0), side(pl->f.size(), 0);
+        std::vector<int> &reads = scratch->reads, &side = scratch->side;
         bool forest = true;
         for (size_t i = 0; i < ns && forest; ++i) {
             std::vector<int> seen;
@@ -667,7 +717,7 @@ void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment,
             for (int id : st.operands)
                 if (pl->f[id].src < 0 && in_smem[id]) side[id] = 1 - mine;
         }
-        std::vector<uint64_t> at(pl->f.size(), 0);      // distance of the table's START (side 0) / END (side 1) from its end of the arena
+        std::vector<uint64_t> &at = scratch->at;        // distance of the table's START (side 0) / END (side 1) from its end of the arena
         uint64_t tops[2] = {0, 0}, best = 0;
         for (size_t i = 0; i < ns && forest; ++i) {
             const PlanStep &st = pl->steps[order[i]];
@@ -693,8 +743,10 @@ void fused_encode(bnpp_ve_plan *pl, const std::vector<int> &order, bool segment,
             if (st.out >= 0 && in_smem[st.out] && last_use[st.out] < 0) tops[side[st.out]] -= (pl->f[st.out].size + 1) & ~1ull;
         }
         if (forest && best > 0 && best < peak && fused_stack_arena()) {
-            for (size_t id = 0; id < pl->f.size(); ++id)
-                if (in_smem[id]) aoff[id] = side[id] == 0 ? at[id] : best - at[id];
+            for (size_t i = 0; i < ns; ++i) {
+                const int id = pl->steps[order[i]].out;
+                if (id >= 0 && in_smem[id]) aoff[id] = side[id] == 0 ? at[id] : best - at[id];
+            }
             peak = best;
         }
     }
@@ -1022,10 +1074,10 @@ void build_segments(bnpp_ve_plan *pl)
     }
     // the programs are independent of one another: encode them on a few host threads (the offset tables of a
     // 1000-bucket network are ~0.5 M words; a one-shot CLI query pays for them inside its timed region)
-    auto encode = [&](size_t i) {
+    auto encode = [&](size_t i, EncodeScratch *sc) {
         std::vector<int> order;
         for (int k = all[i].a; k < all[i].b; ++k) order.push_back(k);
-        fused_encode(pl, order, true, all[i].prog);
+        fused_encode(pl, order, true, all[i].prog, sc);
     };
     const auto tb0 = std::chrono::steady_clock::now();
     const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
@@ -1034,11 +1086,13 @@ void build_segments(bnpp_ve_plan *pl)
         std::vector<std::thread> pool;
         for (unsigned w = 0; w < hw; ++w)
             pool.emplace_back([&] {
-                for (size_t i = next.fetch_add(1); i < all.size(); i = next.fetch_add(1)) encode(i);
+                EncodeScratch sc(pl);
+                for (size_t i = next.fetch_add(1); i < all.size(); i = next.fetch_add(1)) encode(i, &sc);
             });
         for (auto &th : pool) th.join();
-    } else {
-        for (size_t i = 0; i < all.size(); ++i) encode(i);
+    } else if (!all.empty()) {
+        EncodeScratch sc(pl);
+        for (size_t i = 0; i < all.size(); ++i) encode(i, &sc);
     }
     const auto tb1 = std::chrono::steady_clock::now();
     if (getenv("BNPP_TIMING"))
