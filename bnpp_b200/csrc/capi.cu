@@ -39,6 +39,22 @@ int stage_upload(bnpp_ctx *ctx, void *dst_dev, const void *src_host, size_t byte
     return BNPP_OK;
 }
 
+// A contiguous piece of the pinned ring to be filled IN PLACE (nullptr: no ring, or it does not fit) -- for data that
+// is gathered from many small host buffers: gathering it into a fresh pageable vector first pays a page fault per 4 KB.
+// The caller copies out of it with cudaMemcpyAsync on ctx->stream.
+void *stage_reserve(bnpp_ctx *ctx, size_t bytes)
+{
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (!ctx->stage || !bytes || need > ctx->stage_bytes) return nullptr;
+    if (ctx->stage_off + need > ctx->stage_bytes) {
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return nullptr;
+        ctx->stage_off = 0;
+    }
+    void *p = ctx->stage + ctx->stage_off;
+    ctx->stage_off += need;
+    return p;
+}
+
 int cuda_fail(bnpp_ctx *ctx, cudaError_t e, const char *what)
 {
     if (ctx) ctx->last_error = std::string(what) + ": " + cudaGetErrorString(e);

@@ -126,6 +126,7 @@ struct bnpp_ctx {
 namespace bnpp {
 // host -> device copy of a small table, stream-ordered and asynchronous (through the context's pinned ring)
 int stage_upload(bnpp_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+void *stage_reserve(bnpp_ctx *ctx, size_t bytes);
 int fail(bnpp_ctx *ctx, int code, const std::string &msg);
 int cuda_fail(bnpp_ctx *ctx, cudaError_t e, const char *what);
 #define BNPP_CUDA(ctx, expr)                                                   \

@@ -134,7 +134,8 @@ struct bnpp_ve_plan {
     std::vector<int> step_level;            // per step (after build_levels): dependency level; steps of a level never read each other
     std::vector<int> step_task;             // per step: root step of its task (small steps), -1 for wide steps
     // all task programs of the plan in ONE device buffer each (one upload)
-    std::vector<uint32_t> tasks_prog, tasks_tab;
+    std::vector<uint32_t> tasks_prog;
+    size_t tasks_tab_words = 0;         // all offset tables of the tasks, each padded to 4 words (they stay in segs[i].prog.offtab)
     std::vector<bnpp::TaskRecord> tasks_rec;
     struct TaskSlot { uint32_t lo, hi; int kind, index; uint64_t addr; };
     std::vector<TaskSlot> tasks_slots;
@@ -935,7 +936,7 @@ void free_tasks(bnpp_ve_plan *pl)
     pl->tasks_rec_dev = nullptr;
     pl->tasks_uploaded = false;
     pl->tasks_prog.clear();
-    pl->tasks_tab.clear();
+    pl->tasks_tab_words = 0;
     pl->tasks_rec.clear();
     pl->tasks_slots.clear();
     pl->segs.clear();
@@ -1120,25 +1121,20 @@ void build_segments(bnpp_ve_plan *pl)
     }
     const auto tb2 = std::chrono::steady_clock::now();
     // one buffer for all programs, one for all offset tables, one record per task
-    size_t prog_words = 0, tab_words = 0;
-    for (const auto &seg : pl->segs) {
-        prog_words += seg.prog.prog.size();
-        tab_words += seg.prog.offtab.size() + 4;
-    }
+    size_t prog_words = 0;
+    for (const auto &seg : pl->segs) prog_words += seg.prog.prog.size();
     pl->tasks_prog.reserve(prog_words);
-    pl->tasks_tab.reserve(tab_words);
     pl->tasks_rec.reserve(pl->segs.size());
     for (const auto &seg : pl->segs) {
         TaskRecord r;
         r.prog_off = (uint32_t)pl->tasks_prog.size();
-        r.tab_base = (uint32_t)pl->tasks_tab.size();
+        r.tab_base = (uint32_t)pl->tasks_tab_words;
         r.n_steps = seg.prog.n_steps;
         r.arena = seg.prog.arena;
         for (const auto &slot : seg.prog.ptr_slots)
             pl->tasks_slots.push_back({slot.lo + r.prog_off, slot.hi + r.prog_off, slot.kind, slot.index, 0});
         pl->tasks_prog.insert(pl->tasks_prog.end(), seg.prog.prog.begin(), seg.prog.prog.end());
-        pl->tasks_tab.insert(pl->tasks_tab.end(), seg.prog.offtab.begin(), seg.prog.offtab.end());
-        while (pl->tasks_tab.size() % 4) pl->tasks_tab.push_back(0);
+        pl->tasks_tab_words += (seg.prog.offtab.size() + 3) / 4 * 4;
         pl->tasks_rec.push_back(r);
     }
     if (getenv("BNPP_TIMING"))
@@ -1165,13 +1161,23 @@ int upload_tasks(bnpp_ve_plan *pl, const double *const *tables_dev)
     if (!pl->tasks_prog_dev) {
         double *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
         int rc = bnpp_alloc(ctx, pl->tasks_prog.size() / 2 + 18, &p0);      // the kernel prefetches 32 words past a record
-        if (rc == BNPP_OK) rc = bnpp_alloc(ctx, pl->tasks_tab.size() / 2 + 2, &p1);
+        if (rc == BNPP_OK) rc = bnpp_alloc(ctx, pl->tasks_tab_words / 2 + 2, &p1);
         if (rc == BNPP_OK) rc = bnpp_alloc(ctx, pl->tasks_rec.size() * 2 + 2, &p2);
         if (rc != BNPP_OK) return rc;
         pl->tasks_prog_dev = reinterpret_cast<uint32_t *>(p0);
         pl->tasks_tab_dev = reinterpret_cast<uint32_t *>(p1);
         pl->tasks_rec_dev = reinterpret_cast<TaskRecord *>(p2);
-        rc = stage_upload(ctx, pl->tasks_tab_dev, pl->tasks_tab.data(), pl->tasks_tab.size() * sizeof(uint32_t));
+        // the tables are gathered straight into the pinned ring (one copy to the device); too large for it: task by task
+        if (uint32_t *stage = static_cast<uint32_t *>(stage_reserve(ctx, pl->tasks_tab_words * sizeof(uint32_t)))) {
+            for (size_t i = 0; i < pl->segs.size(); ++i)
+                if (!pl->segs[i].prog.offtab.empty())
+                    memcpy(stage + pl->tasks_rec[i].tab_base, pl->segs[i].prog.offtab.data(), pl->segs[i].prog.offtab.size() * sizeof(uint32_t));
+            BNPP_CUDA(ctx, cudaMemcpyAsync(pl->tasks_tab_dev, stage, pl->tasks_tab_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            for (size_t i = 0; i < pl->segs.size() && rc == BNPP_OK; ++i)
+                rc = stage_upload(ctx, pl->tasks_tab_dev + pl->tasks_rec[i].tab_base, pl->segs[i].prog.offtab.data(),
+                                  pl->segs[i].prog.offtab.size() * sizeof(uint32_t));
+        }
         if (rc == BNPP_OK) rc = stage_upload(ctx, pl->tasks_rec_dev, pl->tasks_rec.data(), pl->tasks_rec.size() * sizeof(TaskRecord));
         if (rc != BNPP_OK) return rc;
     }
@@ -1881,7 +1887,7 @@ int bnpp_ve_plan_run(bnpp_ve_plan *pl, const double *const *tables_dev, const ui
         if (timing && pl->runs == 0)
             fprintf(stderr, "bnpp timing: build_segments %.3f ms, upload_tasks %.3f ms (%zu tasks, %zu groups, prog %zu words, tables %zu words)\n",
                     std::chrono::duration<double, std::milli>(t_1 - t_0).count(), std::chrono::duration<double, std::milli>(t_2 - t_1).count(),
-                    pl->segs.size(), pl->groups.size(), pl->tasks_prog.size(), pl->tasks_tab.size());
+                    pl->segs.size(), pl->groups.size(), pl->tasks_prog.size(), pl->tasks_tab_words);
         const bool graphed = pl->use_graph && !pl->profiling && pl->steps.size() > 1 && pl->runs >= 1 &&
                              (!pl->graph_exec || pl->graph_groups == use_groups);
         bool fresh = false;
