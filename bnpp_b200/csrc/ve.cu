@@ -1289,6 +1289,7 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
         rank.set(order[i], (uint64_t)i);
     }
 
+    const auto tc0 = std::chrono::steady_clock::now();
     if (int rc = add_inputs(pl, nfac, scopes, obs_index, rank)) {
         delete pl;
         return fail(ctx, rc, "bad factor scope");
@@ -1305,6 +1306,7 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
     };
     for (int q = 0; q < nfac; ++q) place(q);
 
+    const auto tc1 = std::chrono::steady_clock::now();
     // eliminate in order (code/model.cpp:409-439)
     for (int i = 0; i < n_order; ++i) {
         std::vector<int> ops = bucket[i];
@@ -1334,8 +1336,17 @@ int bnpp_ve_plan_create(bnpp_ctx *ctx, int nfac, const bnpp_scope *scopes, int n
         for (int id : st.operands)
             if (pl->f[id].src < 0 && pl->f[id].last_use == (int)s) live -= 8 * pl->f[id].size;
     }
+    const auto tc2 = std::chrono::steady_clock::now();
     build_exec(pl);
+    const auto tc3 = std::chrono::steady_clock::now();
     if (pl->segments_mode) build_levels(pl);
+    if (getenv("BNPP_TIMING")) {
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        fprintf(stderr, "bnpp timing: plan create: inputs %.3f ms, elimination steps %.3f ms, arena + exec %.3f ms, levels %.3f ms\n",
+                ms(tc0, tc1), ms(tc1, tc2), ms(tc2, tc3), ms(tc3, std::chrono::steady_clock::now()));
+    }
     *out = pl;
     return BNPP_OK;
 }
